@@ -1,0 +1,140 @@
+// hiopLinSolverSymDense on device (B1): matrixChanged() / solve() semantics of
+// src/LinAlg/hiopLinSolverSymDenseLapack.hpp:75-192 and the MAGMA twins hiopLinSolverSymDenseMagma.cpp:120-270, 324-476.
+#include "hb_common.cuh"
+#include "hb_dense.cuh"
+
+struct hb_symdense
+{
+  hb_ctx* ctx = nullptr;
+  int N = 0;
+  double* M = nullptr;      // N x N row-major, upper triangle valid on entry, factor in place
+  double* W = nullptr;      // panel scratch (lazy)
+  double* xbuf = nullptr;   // staging for the *_host variants (lazy)
+  int* ipiv = nullptr;
+  int* info = nullptr;      // device: [0] info, [1..3] inertia
+  int* info_host = nullptr; // pinned
+  int mode = -1;
+  bool factored = false;
+  int n_neg = 0, n_null = 0, n_pos = 0;
+};
+
+namespace {
+constexpr int BLOCKED_BK_MIN_N = 96; // below this the one-CTA unblocked DSYTF2 kernel is faster than panel + trailing launches
+}
+
+extern "C" int hb_symdense_create(hb_ctx* c, int N, hb_symdense** out)
+{
+  HB_REQUIRE(c && out && N >= 0, "hb_symdense_create: bad arguments");
+  HB_CUDA(cudaSetDevice(c->device));
+  hb_symdense* s = new hb_symdense;
+  s->ctx = c;
+  s->N = N;
+  if(cudaMalloc(&s->M, sizeof(double) * (size_t)(N ? N : 1) * (N ? N : 1)) != cudaSuccess) {
+    cudaGetLastError();
+    delete s;
+    return hb_fail(HB_ERR_ALLOC, "hb_symdense_create: cannot allocate the %s system matrix", "N x N");
+  }
+  HB_CUDA(cudaMalloc(&s->ipiv, sizeof(int) * (N + 1)));
+  HB_CUDA(cudaMalloc(&s->info, sizeof(int) * 4));
+  HB_CUDA(cudaMallocHost(&s->info_host, sizeof(int) * 4));
+  HB_CUDA(cudaMemsetAsync(s->M, 0, sizeof(double) * (size_t)(N ? N : 1) * (N ? N : 1), c->stream));
+  *out = s;
+  return HB_OK;
+}
+
+extern "C" int hb_symdense_destroy(hb_symdense* s)
+{
+  if(!s) return HB_OK;
+  cudaSetDevice(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  cudaFree(s->M); cudaFree(s->W); cudaFree(s->xbuf); cudaFree(s->ipiv); cudaFree(s->info);
+  cudaFreeHost(s->info_host);
+  delete s;
+  return HB_OK;
+}
+
+extern "C" double* hb_symdense_matrix(hb_symdense* s) { return s ? s->M : nullptr; }
+
+extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
+{
+  HB_REQUIRE(s, "null handle");
+  HB_REQUIRE(mode == HB_FACT_BUNCH_KAUFMAN || mode == HB_FACT_NOPIV || mode == HB_FACT_CHOLESKY, "hb_symdense_matrix_changed: bad mode");
+  hb_ctx* c = s->ctx;
+  const int N = s->N;
+  s->mode = mode;
+  s->factored = false;
+  if(N == 0) { s->factored = true; s->n_neg = s->n_null = s->n_pos = 0; return 0; }
+  HB_CUDA(cudaMemsetAsync(s->info, 0, sizeof(int) * 4, c->stream));
+  const bool blocked_bk = (mode == HB_FACT_BUNCH_KAUFMAN && N >= BLOCKED_BK_MIN_N);
+  if((mode == HB_FACT_NOPIV || blocked_bk) && !s->W) {
+    if(cudaMalloc(&s->W, sizeof(double) * (size_t)2 * 64 * N) != cudaSuccess) {
+      cudaGetLastError();
+      return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate panel scratch%s", "");
+    }
+  }
+  if(mode == HB_FACT_BUNCH_KAUFMAN) {
+    if(blocked_bk) HB_CHECK(hb_dense_sytrf_blocked(c, N, s->M, N, s->ipiv, s->W, s->info));
+    else HB_CHECK(hb_dense_sytf2(c, N, s->M, N, s->ipiv, s->info));
+  } else {
+    HB_CHECK(hb_dense_factor_blocked(c, N, s->M, N, mode == HB_FACT_NOPIV, s->W, s->info));
+  }
+  HB_CHECK(hb_dense_inertia(c, N, s->M, N, s->ipiv, mode, s->info + 1));
+  HB_CUDA(cudaMemcpyAsync(s->info_host, s->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  s->n_neg = s->info_host[1]; s->n_null = s->info_host[2]; s->n_pos = s->info_host[3];
+  if(s->info_host[0] != 0) return -1; // zero pivot / not SPD: "matrix is singular" (hiopLinSolverSymDenseLapack.hpp:109-116)
+  s->factored = true;
+  if(s->n_null > 0) return -1;        // :166
+  return s->n_neg;
+}
+
+extern "C" int hb_symdense_inertia(hb_symdense* s, int* n_neg, int* n_null, int* n_pos)
+{
+  HB_REQUIRE(s, "null handle");
+  if(n_neg) *n_neg = s->n_neg;
+  if(n_null) *n_null = s->n_null;
+  if(n_pos) *n_pos = s->n_pos;
+  return HB_OK;
+}
+
+extern "C" int hb_symdense_solve(hb_symdense* s, double* x, int nrhs)
+{
+  HB_REQUIRE(s && nrhs >= 0, "hb_symdense_solve: bad arguments");
+  if(s->N == 0 || nrhs == 0) return 1;
+  HB_REQUIRE(x, "hb_symdense_solve: null rhs");
+  if(!s->factored) return hb_fail(HB_ERR_STATE, "hb_symdense_solve: no valid factorization (call hb_symdense_matrix_changed)%s", "");
+  hb_ctx* c = s->ctx;
+  if(s->mode == HB_FACT_BUNCH_KAUFMAN) {
+    HB_CHECK(hb_dense_sytrs(c, s->N, s->M, s->N, s->ipiv, x, s->N, nrhs));
+  } else {
+    for(int r = 0; r < nrhs; r++) HB_CHECK(hb_dense_tri_solve(c, s->N, s->M, s->N, s->mode == HB_FACT_NOPIV, x + (size_t)r * s->N));
+  }
+  return 1;
+}
+
+extern "C" int hb_symdense_matrix_changed_host(hb_symdense* s, const double* M_host, int mode)
+{
+  HB_REQUIRE(s && (M_host || s->N == 0), "hb_symdense_matrix_changed_host: null matrix");
+  if(s->N) HB_CUDA(cudaMemcpyAsync(s->M, M_host, sizeof(double) * (size_t)s->N * s->N, cudaMemcpyHostToDevice, s->ctx->stream));
+  return hb_symdense_matrix_changed(s, mode);
+}
+
+extern "C" int hb_symdense_solve_host(hb_symdense* s, double* x_host, int nrhs)
+{
+  HB_REQUIRE(s && nrhs >= 0, "hb_symdense_solve_host: bad arguments");
+  if(s->N == 0 || nrhs == 0) return 1;
+  hb_ctx* c = s->ctx;
+  static thread_local size_t cap = 0;
+  const size_t need = (size_t)s->N * nrhs;
+  if(!s->xbuf || cap < need) {
+    if(s->xbuf) { HB_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(s->xbuf); s->xbuf = nullptr; }
+    if(cudaMalloc(&s->xbuf, sizeof(double) * need) != cudaSuccess) { cudaGetLastError(); return hb_fail(HB_ERR_ALLOC, "rhs staging allocation failed%s", ""); }
+    cap = need;
+  }
+  HB_CUDA(cudaMemcpyAsync(s->xbuf, x_host, sizeof(double) * need, cudaMemcpyHostToDevice, c->stream));
+  int rc = hb_symdense_solve(s, s->xbuf, nrhs);
+  if(rc != 1) return rc;
+  HB_CUDA(cudaMemcpyAsync(x_host, s->xbuf, sizeof(double) * need, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  return 1;
+}

@@ -1,0 +1,288 @@
+"""Host-side (Python) mirror of the reference's plug-in interfaces for the KKT hot path, on top of the C-ABI.
+
+Names, argument meaning and return conventions follow the reference classes so that the parity tests read like the
+reference's own call sites:
+
+  Context                      one device + one stream (+ optional NCCL communicator)
+  Vector ops (vec_*)           hiopVector methods                        src/LinAlg/hiopVector.hpp
+  LinSolverSymDense            hiopLinSolverSymDense{Lapack,MagmaBuKa,MagmaNopiv}::{matrixChanged, solve}
+                                                                         src/LinAlg/hiopLinSolver.hpp:78-128
+  KKTLinSysLowRank             hiopKKTLinSysLowRank::{update, solveCompressed, computeDirections} with the
+                               hiopHessianLowRank state it owns          src/Optimization/hiopKKTLinSys.cpp:1031-1350
+
+torch is used ONLY as the owner of device buffers (tensor.data_ptr()) and for stream/event plumbing; every
+computation is a call into libhiopb200.so. Nothing here falls back to torch/numpy math.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import EngineError, check
+
+RES_NAMES = ["rx", "rd", "ryc", "ryd", "rxl", "rxu", "rdl", "rdu", "rszl", "rszu", "rsvl", "rsvu"]
+DIR_NAMES = ["x", "d", "yc", "yd", "sxl", "sxu", "sdl", "sdu", "zl", "zu", "vl", "vu"]
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        assert t.dtype == torch.float64 and t.is_contiguous(), "engine buffers are contiguous float64"
+        return ctypes.c_void_p(t.data_ptr())
+    raise TypeError(type(t))
+
+
+class Context:
+    """One GPU, one stream. `with ctx:` makes the engine stream torch's current stream so that tensor allocations,
+    copies and CUDA events are ordered with the engine's kernels."""
+
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise EngineError("hiop_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.lib()
+        self.h = ctypes.c_void_p()
+        check(self.L.hb_ctx_create(device, ctypes.byref(self.h)), "hb_ctx_create")
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self.L.hb_ctx_stream(self.h), device=self.device)
+        self._guard = None
+
+    def __enter__(self):
+        self._guard = torch.cuda.stream(self.stream)
+        self._guard.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        g, self._guard = self._guard, None
+        return g.__exit__(*a)
+
+    def sync(self):
+        check(self.L.hb_ctx_sync(self.h), "hb_ctx_sync")
+
+    def close(self):
+        if self.h:
+            self.L.hb_ctx_destroy(self.h)
+            self.h = None
+
+    def launch_count(self) -> int:
+        return int(self.L.hb_launch_count())
+
+    # -- distributed -----------------------------------------------------------------------------------------
+    def init_comm(self, nranks: int, rank: int, unique_id: bytes | None):
+        buf = ctypes.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self.L.hb_comm_init(self.h, nranks, rank, buf), "hb_comm_init")
+
+    def unique_id(self) -> bytes:
+        buf = ctypes.create_string_buffer(128)
+        check(self.L.hb_comm_unique_id(buf), "hb_comm_unique_id")
+        return buf.raw
+
+    def to_device(self, a) -> torch.Tensor:
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+        with torch.cuda.stream(self.stream):
+            return t.to(self.device, non_blocking=False)
+
+    def zeros(self, *shape) -> torch.Tensor:
+        with torch.cuda.stream(self.stream):
+            return torch.zeros(*shape, dtype=torch.float64, device=self.device)
+
+    # -- hiopVector ops --------------------------------------------------------------------------------------
+    def _v(self, name, n, *args):
+        check(getattr(self.L, name)(self.h, n, *args), name)
+
+    def vec_set(self, y, c): self._v("hb_vec_set", y.numel(), _ptr(y), c)
+    def vec_copy(self, y, x): self._v("hb_vec_copy", y.numel(), _ptr(y), _ptr(x))
+    def vec_scale(self, y, a): self._v("hb_vec_scale", y.numel(), _ptr(y), a)
+    def vec_axpy(self, y, a, x): self._v("hb_vec_axpy", y.numel(), _ptr(y), a, _ptr(x))
+    def vec_axzpy(self, y, a, x, z): self._v("hb_vec_axzpy", y.numel(), _ptr(y), a, _ptr(x), _ptr(z))
+    def vec_axdzpy(self, y, a, x, z): self._v("hb_vec_axdzpy", y.numel(), _ptr(y), a, _ptr(x), _ptr(z))
+    def vec_axdzpy_w_pattern(self, y, a, x, z, s): self._v("hb_vec_axdzpy_w_pattern", y.numel(), _ptr(y), a, _ptr(x), _ptr(z), _ptr(s))
+    def vec_component_mult(self, y, x): self._v("hb_vec_component_mult", y.numel(), _ptr(y), _ptr(x))
+    def vec_component_div(self, y, x): self._v("hb_vec_component_div", y.numel(), _ptr(y), _ptr(x))
+    def vec_component_div_w_pattern(self, y, x, s): self._v("hb_vec_component_div_w_pattern", y.numel(), _ptr(y), _ptr(x), _ptr(s))
+    def vec_invert(self, y): self._v("hb_vec_invert", y.numel(), _ptr(y))
+    def vec_select_pattern(self, y, s): self._v("hb_vec_select_pattern", y.numel(), _ptr(y), _ptr(s))
+    def vec_add_constant(self, y, c): self._v("hb_vec_add_constant", y.numel(), _ptr(y), c)
+    def vec_add_constant_w_pattern(self, y, c, s): self._v("hb_vec_add_constant_w_pattern", y.numel(), _ptr(y), c, _ptr(s))
+    def vec_add_log_barrier_grad(self, y, a, x, s): self._v("hb_vec_add_log_barrier_grad", y.numel(), _ptr(y), a, _ptr(x), _ptr(s))
+    def vec_add_linear_damping_term(self, y, ixl, ixu, a, ct): self._v("hb_vec_add_linear_damping_term", y.numel(), _ptr(y), _ptr(ixl), _ptr(ixu), a, ct)
+
+    def _r(self, name, n, *args) -> float:
+        out = ctypes.c_double()
+        check(getattr(self.L, name)(self.h, n, *args, ctypes.byref(out)), name)
+        return out.value
+
+    def vec_dot(self, x, y): return self._r("hb_vec_dot", x.numel(), _ptr(x), _ptr(y))
+    def vec_twonorm(self, x): return self._r("hb_vec_twonorm", x.numel(), _ptr(x))
+    def vec_infnorm(self, x): return self._r("hb_vec_infnorm", x.numel(), _ptr(x))
+    def vec_onenorm(self, x): return self._r("hb_vec_onenorm", x.numel(), _ptr(x))
+    def vec_min_w_pattern(self, x, s): return self._r("hb_vec_min_w_pattern", x.numel(), _ptr(x), _ptr(s))
+    def vec_log_barrier(self, x, s): return self._r("hb_vec_log_barrier", x.numel(), _ptr(x), _ptr(s))
+    def vec_linear_damping_term(self, x, ixl, ixu, mu, kd): return self._r("hb_vec_linear_damping_term", x.numel(), _ptr(x), _ptr(ixl), _ptr(ixu), mu, kd)
+    def vec_fraction_to_bdry(self, x, dx, tau, s=None): return self._r("hb_vec_fraction_to_bdry", x.numel(), _ptr(x), _ptr(dx), tau, _ptr(s))
+
+    def mat_times_vec(self, A, beta, y, alpha, x):
+        m, n = A.shape
+        check(self.L.hb_mat_times_vec(self.h, m, n, _ptr(A), n, beta, _ptr(y), alpha, _ptr(x)), "hb_mat_times_vec")
+
+    def mat_trans_times_vec(self, A, beta, y, alpha, x):
+        m, n = A.shape
+        check(self.L.hb_mat_trans_times_vec(self.h, m, n, _ptr(A), n, beta, _ptr(y), alpha, _ptr(x)), "hb_mat_trans_times_vec")
+
+
+class LinSolverSymDense:
+    """hiopLinSolverSymDense: owns the N x N row-major system matrix (upper triangle valid), `matrixChanged()` returns
+    the number of negative eigenvalues or -1, `solve(x)` overwrites the rhs (src/LinAlg/hiopLinSolver.hpp:78-128)."""
+
+    BUNCH_KAUFMAN, NOPIV, CHOLESKY = _lib.HB_FACT_BUNCH_KAUFMAN, _lib.HB_FACT_NOPIV, _lib.HB_FACT_CHOLESKY
+
+    def __init__(self, ctx: Context, n: int, mode: int = _lib.HB_FACT_BUNCH_KAUFMAN):
+        self.ctx, self.n, self.mode = ctx, n, mode
+        self.h = ctypes.c_void_p()
+        check(ctx.L.hb_symdense_create(ctx.h, n, ctypes.byref(self.h)), "hb_symdense_create")
+        self._mptr = ctx.L.hb_symdense_matrix(self.h)
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_symdense_destroy(self.h)
+            self.h = None
+
+    def set_matrix(self, M: torch.Tensor):
+        """Fills sysMatrix() from a device tensor (what the KKT class's build_kkt_matrix does in place)."""
+        assert M.shape == (self.n, self.n)
+        check(self.ctx.L.hb_memcpy_d2d(self.ctx.h, ctypes.c_void_p(self._mptr), _ptr(M.contiguous()), 8 * self.n * self.n), "memcpy")
+
+    def matrixChanged(self) -> int:
+        rc = self.ctx.L.hb_symdense_matrix_changed(self.h, self.mode)
+        if rc < -1:
+            check(rc, "hb_symdense_matrix_changed")
+        return rc
+
+    def matrixChanged_host(self, M: np.ndarray) -> int:
+        M = np.ascontiguousarray(M, dtype=np.float64)
+        rc = self.ctx.L.hb_symdense_matrix_changed_host(self.h, M.ctypes.data_as(ctypes.c_void_p), self.mode)
+        if rc < -1:
+            check(rc, "hb_symdense_matrix_changed_host")
+        return rc
+
+    def inertia(self):
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        check(self.ctx.L.hb_symdense_inertia(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)), "hb_symdense_inertia")
+        return a.value, b.value, c.value
+
+    def solve(self, x: torch.Tensor) -> bool:
+        nrhs = x.numel() // max(self.n, 1) if self.n else 0
+        rc = self.ctx.L.hb_symdense_solve(self.h, _ptr(x), nrhs)
+        if rc < 0:
+            check(rc, "hb_symdense_solve")
+        return rc == 1
+
+    def solve_host(self, x: np.ndarray) -> bool:
+        assert x.dtype == np.float64 and x.flags["C_CONTIGUOUS"]
+        nrhs = x.size // max(self.n, 1) if self.n else 0
+        rc = self.ctx.L.hb_symdense_solve_host(self.h, x.ctypes.data_as(ctypes.c_void_p), nrhs)
+        if rc < 0:
+            check(rc, "hb_symdense_solve_host")
+        return rc == 1
+
+
+class KKTLinSysLowRank:
+    """hiopKKTLinSysLowRank with the hiopHessianLowRank state it drives.
+
+    Reference call order per IPM iteration (src/Optimization/hiopAlgFilterIPM.cpp:1215-1226):
+        Hess->update(...)  -> set_secant(l, sigma, St, Yt, L, D)
+        kkt->update(iter, grad_f, Jac_c, Jac_d, Hess) -> set_jacobian(Jc, Jd); update(iterate blocks)
+        kkt->computeDirections(resid, dir)  -> compute_directions(res) / solveCompressed(rx, ryc, ryd)
+    """
+
+    def __init__(self, ctx: Context, n_local: int, m_eq: int, m_ineq: int, l_max: int = 6):
+        self.ctx, self.n, self.m_eq, self.m_ineq, self.l_max = ctx, n_local, m_eq, m_ineq, l_max
+        self.h = ctypes.c_void_p()
+        check(ctx.L.hb_lowrank_create(ctx.h, n_local, m_eq, m_ineq, l_max, ctypes.byref(self.h)), "hb_lowrank_create")
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_lowrank_destroy(self.h)
+            self.h = None
+
+    def set_patterns(self, ixl, ixu, idl, idu):
+        self._keep["pat"] = (ixl, ixu, idl, idu)
+        check(self.ctx.L.hb_lowrank_set_patterns(self.h, _ptr(ixl), _ptr(ixu), _ptr(idl), _ptr(idu)), "hb_lowrank_set_patterns")
+
+    def set_jacobian(self, Jc, Jd):
+        self._keep["jac"] = (Jc, Jd)
+        check(self.ctx.L.hb_lowrank_set_jacobian(self.h, _ptr(Jc), _ptr(Jd)), "hb_lowrank_set_jacobian")
+
+    def set_secant(self, sigma: float, St, Yt, L: np.ndarray, D: np.ndarray):
+        l = 0 if St is None else St.shape[0]
+        self._keep["sec"] = (St, Yt)
+        Lh = np.ascontiguousarray(L, dtype=np.float64)
+        Dh = np.ascontiguousarray(D, dtype=np.float64)
+        check(self.ctx.L.hb_lowrank_set_secant(self.h, l, float(sigma), _ptr(St) if l else None, _ptr(Yt) if l else None,
+                                               Lh.ctypes.data_as(ctypes.c_void_p), Dh.ctypes.data_as(ctypes.c_void_p)),
+              "hb_lowrank_set_secant")
+
+    def update(self, zl, sxl, zu, sxu, vl, sdl, vu, sdu) -> bool:
+        self._keep["it"] = (zl, sxl, zu, sxu, vl, sdl, vu, sdu)
+        check(self.ctx.L.hb_lowrank_update(self.h, *[_ptr(t) for t in (zl, sxl, zu, sxu, vl, sdl, vu, sdu)]), "hb_lowrank_update")
+        return True
+
+    def condense(self):
+        check(self.ctx.L.hb_lowrank_condense(self.h), "hb_lowrank_condense")
+
+    def solveCompressed(self, rx, ryc, ryd, dx, dyc, dyd) -> bool:
+        """rx is clobbered, like in the reference (hiopKKTLinSys.cpp:1178)."""
+        rc = self.ctx.L.hb_lowrank_solve_compressed(self.h, *[_ptr(t) for t in (rx, ryc, ryd, dx, dyc, dyd)])
+        if rc == -4:
+            return False
+        check(rc, "hb_lowrank_solve_compressed")
+        return True
+
+    def computeDirections(self, res: dict, dirs: dict) -> bool:
+        R = (ctypes.c_void_p * 12)(*[_ptr(res[k]) for k in RES_NAMES])
+        Dp = (ctypes.c_void_p * 12)(*[_ptr(dirs[k]) for k in DIR_NAMES])
+        rc = self.ctx.L.hb_lowrank_compute_directions(self.h, R, Dp)
+        if rc == -4:
+            return False
+        check(rc, "hb_lowrank_compute_directions")
+        return True
+
+    def hess_solve(self, rhs, x):
+        check(self.ctx.L.hb_lowrank_hess_solve(self.h, _ptr(rhs), _ptr(x)), "hb_lowrank_hess_solve")
+
+    def hess_times_vec(self, beta, y, alpha, x, add_log_term=False):
+        check(self.ctx.L.hb_lowrank_hess_times_vec(self.h, beta, _ptr(y), alpha, _ptr(x), int(add_log_term)), "hb_lowrank_hess_times_vec")
+
+    def _readback(self, fn, count):
+        p = getattr(self.ctx.L, fn)(self.h)
+        out = np.empty(count, dtype=np.float64)
+        check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(p), 8 * count), "memcpy")
+        self.ctx.sync()
+        return out
+
+    def Dx(self): return self._readback("hb_lowrank_Dx", self.n)
+    def DhInv(self): return self._readback("hb_lowrank_DhInv", self.n)
+    def Dd_inv(self): return self._readback("hb_lowrank_Dd_inv", self.m_ineq)
+    def N(self):
+        m = self.m_eq + self.m_ineq
+        return self._readback("hb_lowrank_N", m * m).reshape(m, m)
+
+    def last_solve_stats(self):
+        a, b = ctypes.c_int(), ctypes.c_double()
+        check(self.ctx.L.hb_lowrank_last_solve_stats(self.h, ctypes.byref(a), ctypes.byref(b)), "hb_lowrank_last_solve_stats")
+        return a.value, b.value
+
+    def kkt_system_host(self, Jc, Jd, it: dict, rx, ryc, ryd, dx, dyc, dyd):
+        """Whole system from HOST numpy buffers (pinned or pageable); Jc/Jd may be None to reuse the resident Jacobian."""
+        def hp(a):
+            if a is None:
+                return None
+            assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+            return a.ctypes.data_as(ctypes.c_void_p)
+        args = [hp(Jc), hp(Jd)] + [hp(it[k]) for k in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu")] + \
+               [hp(a) for a in (rx, ryc, ryd, dx, dyc, dyd)]
+        check(self.ctx.L.hb_lowrank_kkt_system_host(self.h, *args), "hb_lowrank_kkt_system_host")

@@ -1,0 +1,210 @@
+/* hiopb200.h -- C-ABI of the B200-native (sm_100a) engine for HiOp's KKT assemble + factor + solve hot path.
+ *
+ * Drop-in boundary: every entry point below replaces one reference interface (cited as file:line relative to
+ * the LLNL/hiop tree). The library is libhiopb200.so; INTEGRATION.md shows the C++ adapter classes
+ * (hiopLinSolverSymDenseB200, hiopKKTLinSysLowRankB200, hiopVectorB200) a HiOp maintainer would add on top.
+ *
+ * Conventions (copied from the reference's own C interface, src/Interface/hiopInterface.h): plain pointers and
+ * sizes, `int` status returns (HB_OK = 0, negative = error; hb_last_error() gives the text), no exceptions cross the
+ * boundary, opaque handles owned by the engine, inputs owned by the caller.
+ *   - All `double*` / `int*` arguments are DEVICE pointers unless the function name ends in `_host` or the
+ *     parameter is documented as host.
+ *   - All arithmetic is IEEE FP64; patterns ("select" vectors) are FP64 0.0/1.0 as in the reference
+ *     (src/LinAlg/hiopVectorPar.cpp:782).
+ *   - Dense matrices are row-major like hiopMatrixDenseRowMajor (src/LinAlg/hiopMatrixDenseRowMajor.cpp:86-96).
+ *   - Element counts / offsets are 64-bit (`long long`); the reference's `int` indexing cannot address the n=4e6,
+ *     m=4000 configuration.
+ *   - Every context owns one CUDA stream; calls are asynchronous on that stream unless they return a host scalar.
+ *   - There is no CPU fallback anywhere: without a CUDA device hb_ctx_create fails with HB_ERR_CUDA.
+ */
+#ifndef HIOPB200_H
+#define HIOPB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_INVALID (-1)   /* bad argument */
+#define HB_ERR_CUDA (-2)      /* CUDA runtime error (message in hb_last_error) */
+#define HB_ERR_ALLOC (-3)     /* device allocation failed */
+#define HB_ERR_NUMERIC (-4)   /* factorization broke down (not SPD / zero pivot) */
+#define HB_ERR_STATE (-5)     /* call order violated (e.g. solve before condense) */
+#define HB_ERR_COMM (-6)      /* NCCL not available / communicator error */
+
+typedef struct hb_ctx hb_ctx;
+typedef struct hb_lowrank hb_lowrank;
+typedef struct hb_symdense hb_symdense;
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Context, memory, streams
+ * ------------------------------------------------------------------------------------------------------------ */
+const char* hb_version(void);
+const char* hb_last_error(void);
+/* number of kernel launches issued by this library since load (all contexts); feeds bench.py's gpu_launches */
+long long hb_launch_count(void);
+
+/* Replaces the ExecSpace/MemBackend plumbing (src/ExecBackends/) for this path: one device, one stream. */
+int hb_ctx_create(int device, hb_ctx** out);
+int hb_ctx_destroy(hb_ctx* ctx);
+int hb_ctx_sync(hb_ctx* ctx);
+/* the cudaStream_t of the context (so a host framework can order its own work/events against it) */
+void* hb_ctx_stream(hb_ctx* ctx);
+int hb_ctx_device(hb_ctx* ctx);
+
+int hb_malloc(hb_ctx* ctx, size_t bytes, void** dptr);
+int hb_free(hb_ctx* ctx, void* dptr);
+int hb_malloc_host(hb_ctx* ctx, size_t bytes, void** hptr); /* pinned */
+int hb_free_host(hb_ctx* ctx, void* hptr);
+int hb_memcpy_h2d(hb_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes); /* async on the ctx stream */
+int hb_memcpy_d2h(hb_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes); /* async on the ctx stream */
+int hb_memcpy_d2d(hb_ctx* ctx, void* dst_dev, const void* src_dev, size_t bytes);
+int hb_memset(hb_ctx* ctx, void* dst_dev, int byte, size_t bytes);
+
+/* Multi-GPU: column (n) partition exactly like the reference's MPI layout (src/Optimization/hiopHessianLowRank.hpp:88-89).
+ * The 128-byte NCCL unique id is created on rank 0 (hb_comm_unique_id) and broadcast by the host program.
+ * After hb_comm_init every reduction the reference does with MPI_Allreduce on this path
+ * (src/Optimization/hiopHessianLowRank.cpp:459,590,591; src/LinAlg/hiopMatrixDenseRowMajor.cpp:487;
+ * src/LinAlg/hiopVectorPar.cpp:474-548) is done with ncclAllReduce on the context stream. */
+int hb_comm_unique_id(void* id128_host);
+int hb_comm_init(hb_ctx* ctx, int nranks, int rank, const void* id128_host);
+int hb_comm_size(hb_ctx* ctx);
+int hb_comm_rank(hb_ctx* ctx);
+/* in-place sum all-reduce of `count` doubles on the context stream (no-op for a single rank) */
+int hb_allreduce_sum(hb_ctx* ctx, double* buf_dev, long long count);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hiopVector elementwise ops + reductions (B3; src/LinAlg/hiopVector.hpp:62-1017, oracle: hiopVectorPar.cpp)
+ * One launch each; 128-bit vectorised, grid-stride over 148 x k CTAs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int hb_vec_set(hb_ctx*, long long n, double* y, double c);                                  /* setToConstant */
+int hb_vec_copy(hb_ctx*, long long n, double* y, const double* x);                          /* copyFrom */
+int hb_vec_scale(hb_ctx*, long long n, double* y, double alpha);                            /* scale        :657 */
+int hb_vec_axpy(hb_ctx*, long long n, double* y, double alpha, const double* x);            /* axpy         :662-670 */
+int hb_vec_axzpy(hb_ctx*, long long n, double* y, double alpha, const double* x, const double* z);   /* :710-734 */
+int hb_vec_axdzpy(hb_ctx*, long long n, double* y, double alpha, const double* x, const double* z);  /* :736-765 */
+int hb_vec_axdzpy_w_pattern(hb_ctx*, long long n, double* y, double alpha, const double* x, const double* z,
+                            const double* select);                                          /* :767-790 */
+int hb_vec_component_mult(hb_ctx*, long long n, double* y, const double* x);                /* :564-572 */
+int hb_vec_component_div(hb_ctx*, long long n, double* y, const double* x);                 /* :574-582 */
+int hb_vec_component_div_w_pattern(hb_ctx*, long long n, double* y, const double* x, const double* select); /* :584-592 */
+int hb_vec_invert(hb_ctx*, long long n, double* y);                                         /* :852-860 */
+int hb_vec_select_pattern(hb_ctx*, long long n, double* y, const double* select);           /* :1063-1071 */
+int hb_vec_add_constant(hb_ctx*, long long n, double* y, double c);                         /* :793-797 */
+int hb_vec_add_constant_w_pattern(hb_ctx*, long long n, double* y, double c, const double* select); /* :799-804 */
+int hb_vec_add_log_barrier_grad(hb_ctx*, long long n, double* y, double alpha, const double* x, const double* select); /* :893-905 */
+int hb_vec_add_linear_damping_term(hb_ctx*, long long n, double* y, const double* ixl, const double* ixu,
+                                   double alpha, double ct);                                /* :927-944 */
+/* reductions: result written to *out_host after a stream sync (and an NCCL all-reduce when a communicator is set,
+ * SUM for dot/twonorm^2/onenorm/logbarrier/damping, MAX for infnorm, MIN for min/fraction-to-boundary) */
+int hb_vec_dot(hb_ctx*, long long n, const double* x, const double* y, double* out_host);   /* dotProductWith :480-499 */
+int hb_vec_twonorm(hb_ctx*, long long n, const double* x, double* out_host);                /* twonorm   :463-478 */
+int hb_vec_infnorm(hb_ctx*, long long n, const double* x, double* out_host);                /* infnorm   :501-521 */
+int hb_vec_onenorm(hb_ctx*, long long n, const double* x, double* out_host);                /* onenorm   :540-553 */
+int hb_vec_min_w_pattern(hb_ctx*, long long n, const double* x, const double* select, double* out_host); /* :821-839 */
+int hb_vec_log_barrier(hb_ctx*, long long n, const double* x, const double* select, double* out_host);   /* :863-881 */
+int hb_vec_linear_damping_term(hb_ctx*, long long n, const double* x, const double* ixl, const double* ixu,
+                               double mu, double kappa_d, double* out_host);                /* :907-925 */
+int hb_vec_fraction_to_bdry(hb_ctx*, long long n, const double* x, const double* dx, double tau,
+                            const double* select_or_null, double* out_host);                /* :1017-1061 */
+
+/* hiopMatrixDenseRowMajor::timesVec / transTimesVec (src/LinAlg/hiopMatrixDenseRowMajor.cpp:436-528):
+ * A is m x n row-major with leading dimension lda (elements). With a communicator the m-vector result of
+ * hb_mat_times_vec is all-reduced and beta*y is applied on rank 0 only (:464-467). */
+int hb_mat_times_vec(hb_ctx*, int m, long long n, const double* A, long long lda, double beta, double* y, double alpha,
+                     const double* x);
+int hb_mat_trans_times_vec(hb_ctx*, int m, long long n, const double* A, long long lda, double beta, double* y,
+                           double alpha, const double* x);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hiopLinSolverSymDense (B1; src/LinAlg/hiopLinSolver.hpp:78-128, LAPACK twin hiopLinSolverSymDenseLapack.hpp:75-192,
+ * MAGMA twins hiopLinSolverSymDenseMagma.cpp:120-270, 324-476)
+ * ------------------------------------------------------------------------------------------------------------ */
+#define HB_FACT_BUNCH_KAUFMAN 0 /* pivoted LDL^T (DSYTRF / magma_dsytrf_gpu semantics), inertia from 1x1/2x2 pivots */
+#define HB_FACT_NOPIV 1         /* LDL^T without pivoting (magma_dsytrf_nopiv_gpu, linsol_mode=speculative) */
+#define HB_FACT_CHOLESKY 2      /* LL^T for SPD systems (DPOTRF; duals LSQ + condensed QN system) */
+
+int hb_symdense_create(hb_ctx* ctx, int N, hb_symdense** out);
+int hb_symdense_destroy(hb_symdense* s);
+/* device pointer of the N x N row-major system matrix M_ (sysMatrix(), hiopLinSolver.cpp:99-102); the caller fills
+ * its UPPER triangle before each hb_symdense_matrix_changed (hiopKKTLinSysMDS.cpp:196-206). */
+double* hb_symdense_matrix(hb_symdense* s);
+/* matrixChanged(): factorizes in place. Returns the reference's value: >= 0 number of negative eigenvalues,
+ * -1 if a null pivot (|d| < 1e-14, hiopLinSolverSymDenseLapack.hpp:154-166) or a breakdown was met.
+ * Values <= -2 are HB_ERR_* codes. */
+int hb_symdense_matrix_changed(hb_symdense* s, int mode);
+/* inertia of the last factorization (host ints): negative, null, positive */
+int hb_symdense_inertia(hb_symdense* s, int* n_neg, int* n_null, int* n_pos);
+/* solve(x): in-place solve with nrhs right-hand sides stored one after the other (each N doubles, device).
+ * Returns 1 on success, 0 on failure (bool semantics of hiopLinSolver::solve), negative HB_ERR_* on misuse. */
+int hb_symdense_solve(hb_symdense* s, double* x, int nrhs);
+/* host-buffer convenience used by the C++ adapter when mem_space is host: uploads the upper triangle, factorizes */
+int hb_symdense_matrix_changed_host(hb_symdense* s, const double* M_host, int mode);
+int hb_symdense_solve_host(hb_symdense* s, double* x_host, int nrhs);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hiopKKTLinSysLowRank + hiopHessianLowRank (B2; src/Optimization/hiopKKTLinSys.cpp:1031-1350,
+ * src/Optimization/hiopHessianLowRank.cpp:221-630, 974-1059)
+ * n_local columns on this rank (all n-vectors and the columns of J, S_t, Y_t are sharded; m-, l-sized data are
+ * replicated). m = m_eq + m_ineq constraints, l <= l_max secant pairs.
+ * ------------------------------------------------------------------------------------------------------------ */
+int hb_lowrank_create(hb_ctx* ctx, long long n_local, int m_eq, int m_ineq, int l_max, hb_lowrank** out);
+int hb_lowrank_destroy(hb_lowrank* k);
+/* bound patterns ixl, ixu (n_local) and idl, idu (m_ineq): get_ixl()... of hiopNlpFormulation. Borrowed. */
+int hb_lowrank_set_patterns(hb_lowrank* k, const double* ixl, const double* ixu, const double* idl, const double* idu);
+/* Jacobians Jac_c (m_eq x n_local) and Jac_d (m_ineq x n_local), row-major, leading dimension n_local. Borrowed until
+ * the next call. If Jd == Jc + m_eq*n_local the engine uses [Jc;Jd] in place (no copy; the reference copies m x n
+ * doubles per solve, hiopKKTLinSys.cpp:1127-1128), otherwise it packs them into an internal m x n_local buffer. */
+int hb_lowrank_set_jacobian(hb_lowrank* k, const double* Jc, const double* Jd);
+/* Compact-BFGS state as hiopHessianLowRank::update leaves it (hiopHessianLowRank.cpp:262-388): S_t, Y_t are l x n_local
+ * row-major device arrays (borrowed); L (l x l row-major, strictly lower) and D (l) are HOST arrays (they are
+ * "local" DEFAULT-space objects in the reference too, hiopHessianLowRank.cpp:85-87); sigma = B0 scaling. */
+int hb_lowrank_set_secant(hb_lowrank* k, int l, double sigma, const double* St, const double* Yt, const double* L_host,
+                          const double* D_host);
+/* update(): Dx = zl/sxl|ixl + zu/sxu|ixu, DhInv = 1/(sigma+Dx), Dd = vl/sdl|idl + vu/sdu|idu, Dd_inv = 1/Dd in ONE fused
+ * pass (hiopKKTLinSys.cpp:1057-1094 + hiopHessianLowRank.cpp:221-233; 7 n-passes in the reference). Borrows the
+ * iterate pointers until the next update (they are read again by hb_lowrank_compute_directions). */
+int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* sxl, const double* zu, const double* sxu,
+                      const double* vl, const double* sdl, const double* vu, const double* sdu);
+/* Forms V (2l x 2l), factorizes it (Bunch-Kaufman), forms N = J (B_k+D_x)^{-1} J^T + blkdiag(0, Dd_inv) with ONE pass
+ * over J (fused W, S1, Y1, V-blocks; FP64 tensor-core SYRK), all-reduces it across ranks and Cholesky-factorizes it
+ * with equilibration (symMatTimesInverseTimesMatTrans hiopHessianLowRank.cpp:549-630, updateInternalBFGSRepresentation
+ * :400-485, DPOSVX('E') hiopKKTLinSys.cpp:1228). The factor is cached until the next update/set_* call.
+ * Returns HB_ERR_NUMERIC if N is not numerically SPD. */
+int hb_lowrank_condense(hb_lowrank* k);
+/* solveCompressed(rx,ryc,ryd -> dx,dyc,dyd) (hiopKKTLinSys.cpp:1110-1190) incl. the residual-driven refinement of
+ * solveWithRefin (:1192-1350: ||rhs - N x||_inf < 1e-8, <= 3 corrections). Condenses first if the cache is stale.
+ * Like the reference, rx is used as scratch and overwritten (:1178). */
+int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const double* ryc, const double* ryd, double* dx, double* dyc,
+                                double* dyd);
+/* computeDirections (hiopKKTLinSysCompressedXYcYd::computeDirections hiopKKTLinSys.cpp:585-691 +
+ * compute_directions_for_full_space :218-309): the 12 residual blocks -> the 12 direction blocks.
+ * res = {rx, rd, ryc, ryd, rxl, rxu, rdl, rdu, rszl, rszu, rsvl, rsvu}; dir = {x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu}
+ * (HOST arrays of 12 DEVICE pointers). Residuals are not modified. */
+int hb_lowrank_compute_directions(hb_lowrank* k, const double* const* res, double* const* dir);
+/* x = (B_k + D_x)^{-1} rhs  (hiopHessianLowRank::solve :495-540) */
+int hb_lowrank_hess_solve(hb_lowrank* k, const double* rhs, double* x);
+/* y = beta*y + alpha*(B_k [+ D_x]) x in the compact form (same operator as the recursive timesVecCmn :974-1059) */
+int hb_lowrank_hess_times_vec(hb_lowrank* k, double beta, double* y, double alpha, const double* x, int add_log_term);
+/* read-backs (device pointers owned by the engine; valid until destroy): Dx, DhInv (n_local), Dd_inv (m_ineq),
+ * N (m x m row-major, full symmetric storage, UNfactorized copy) */
+const double* hb_lowrank_Dx(hb_lowrank* k);
+const double* hb_lowrank_DhInv(hb_lowrank* k);
+const double* hb_lowrank_Dd_inv(hb_lowrank* k);
+const double* hb_lowrank_N(hb_lowrank* k);
+/* statistics of the last solve: refinement steps taken, last residual inf-norm (host) */
+int hb_lowrank_last_solve_stats(hb_lowrank* k, int* n_refine, double* resid_inf);
+/* One whole KKT system from HOST buffers (the e2e path of bench.py and of the C++ adapter when HiOp keeps its data in
+ * host memory): H2D of the iterate blocks, (optionally) J and rhs, update + condense + solve, D2H of dx,dyc,dyd.
+ * J_host may be NULL to reuse the device-resident Jacobian from the previous call. */
+int hb_lowrank_kkt_system_host(hb_lowrank* k, const double* Jc_host, const double* Jd_host, const double* zl,
+                               const double* sxl, const double* zu, const double* sxu, const double* vl, const double* sdl,
+                               const double* vu, const double* sdu, const double* rx, const double* ryc, const double* ryd,
+                               double* dx, double* dyc, double* dyd);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HIOPB200_H */

@@ -1,0 +1,201 @@
+"""TEST INFRASTRUCTURE ONLY -- ctypes binding of oracle/_ref/libhiop_ref_harness.so, i.e. the UNMODIFIED
+reference CPU path (compiled by oracle/Makefile from /root/reference, driven by oracle/ref_harness.cpp).
+Used to (1) pin the numpy/C restatement in kkt_oracle.py, (2) generate tests/golden/*.npz, and (3) as the
+"reference" cpu_baseline / --impl reference arm of bench.py. Never imported by the product."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libhiop_ref_harness.so")
+_LIB = None
+
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+
+
+def available() -> bool:
+    return os.path.exists(SO)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = ctypes.CDLL(SO)
+        L.ref_qn_create.restype = ctypes.c_void_p
+        L.ref_qn_create.argtypes = [ctypes.c_int] * 4 + [dp] * 4
+        L.ref_qn_destroy.argtypes = [ctypes.c_void_p]
+        L.ref_qn_sizes.argtypes = [ctypes.c_void_p, ip]
+        L.ref_qn_set_iterate.argtypes = [ctypes.c_void_p] + [dp] * 8
+        L.ref_qn_set_jac.argtypes = [ctypes.c_void_p, dp, dp]
+        L.ref_qn_set_secant.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, dp, dp, dp, dp]
+        L.ref_qn_update.argtypes = [ctypes.c_void_p, dp, dp, dp, dp]
+        L.ref_qn_condense.argtypes = [ctypes.c_void_p, dp, dp]
+        L.ref_qn_solve_compressed.argtypes = [ctypes.c_void_p] + [dp] * 7
+        L.ref_qn_solve_compressed.restype = ctypes.c_int
+        L.ref_qn_hess_solve.argtypes = [ctypes.c_void_p, dp, dp]
+        L.ref_qn_hess_times_vec.argtypes = [ctypes.c_void_p, ctypes.c_double, dp, ctypes.c_double, dp, ctypes.c_int]
+        L.ref_qn_compute_directions.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp)]
+        L.ref_qn_compute_directions.restype = ctypes.c_int
+        L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
+        L.ref_symdense_factor_solve.restype = ctypes.c_int
+        L.ref_vec_op.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double]
+        L.ref_vec_op.restype = ctypes.c_double
+        L.ref_mat_times_vec.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, dp, ctypes.c_double, dp]
+        L.ref_mat_trans_times_vec.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_double, dp, ctypes.c_double, dp]
+        L.ref_mat_trans_add_to_sym_upper.argtypes = [ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int,
+                                                     ctypes.c_double, ctypes.c_int, dp]
+        L.ref_mat_add_upper_to_sym_upper.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_double, ctypes.c_int, dp]
+        L.ref_mat_add_sub_diagonal.argtypes = [ctypes.c_int, dp, ctypes.c_int, ctypes.c_double, ctypes.c_int, dp]
+        L.ref_sp_add_MDinvMtrans.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, dp, ctypes.c_int,
+                                             ctypes.c_double, dp, ctypes.c_int, dp]
+        L.ref_sp_add_MDinvNtrans.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ip, ip, dp,
+                                             ctypes.c_int, ctypes.c_int, ip, ip, dp,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, dp]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(dp)
+
+
+def _i(a):
+    a = np.ascontiguousarray(a, dtype=np.int32)
+    return a, a.ctypes.data_as(ip)
+
+
+# op codes of ref_vec_op (kept in sync with the enum in ref_harness.cpp)
+OPS = dict(axdzpy_w_pattern=1, axzpy=2, axdzpy=3, component_mult=4, component_div=5, component_div_w_sel=6,
+           invert=7, select_pattern=8, add_constant=9, add_constant_w_sel=10, scale=11, axpy=12,
+           add_logbar_grad=13, add_lin_damping=14, twonorm=20, dot=21, infnorm=22, onenorm=23, logbarrier=24,
+           lin_damping_term=25, min_w_pattern=26, frac_to_bdry=27, frac_to_bdry_w_sel=28, sum=29)
+
+
+def vec_op(op, y, x=None, z=None, sel=None, alpha=0.0, beta=0.0):
+    """Runs one hiopVectorPar method; returns (y_out, scalar)."""
+    n = y.size
+    yy = np.array(y, dtype=np.float64)
+    keep = [yy]
+
+    def opt(a):
+        if a is None:
+            return None
+        arr, ptr = _d(a)
+        keep.append(arr)
+        return ptr
+
+    r = lib().ref_vec_op(OPS[op], n, yy.ctypes.data_as(dp), opt(x), opt(z), opt(sel), alpha, beta)
+    return yy, r
+
+
+class RefQn:
+    """One quasi-Newton KKT system replayed through the reference's own classes."""
+
+    def __init__(self, n, m_eq, m_ineq, lmax, ixl, ixu, idl, idu):
+        self.n, self.meq, self.mineq, self.lmax = n, m_eq, m_ineq, lmax
+        a = [_d(v) for v in (ixl, ixu, idl if m_ineq else np.zeros(1), idu if m_ineq else np.zeros(1))]
+        self.h = lib().ref_qn_create(n, m_eq, m_ineq, lmax, *[p for _, p in a])
+        sz = (ctypes.c_int * 5)()
+        lib().ref_qn_sizes(self.h, sz)
+        assert (sz[0], sz[1], sz[2]) == (n, m_eq, m_ineq), list(sz)
+
+    def close(self):
+        if self.h:
+            lib().ref_qn_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_iterate(self, sxl, sxu, zl, zu, sdl, sdu, vl, vu):
+        a = [_d(v) for v in (sxl, sxu, zl, zu, sdl, sdu, vl, vu)]
+        lib().ref_qn_set_iterate(self.h, *[p for _, p in a])
+
+    def set_jac(self, Jc, Jd):
+        a, pa = _d(Jc)
+        b, pb = _d(Jd)
+        lib().ref_qn_set_jac(self.h, pa, pb)
+
+    def set_secant(self, sigma, St, Yt, L, D):
+        l = St.shape[0]
+        a = [_d(v) for v in (St, Yt, L, D)]
+        lib().ref_qn_set_secant(self.h, l, float(sigma), *[p for _, p in a])
+
+    def update(self):
+        Dx = np.zeros(self.n)
+        DhInv = np.zeros(self.n)
+        Ddinv = np.zeros(self.mineq)
+        t = np.zeros(4)
+        lib().ref_qn_update(self.h, Dx.ctypes.data_as(dp), DhInv.ctypes.data_as(dp), Ddinv.ctypes.data_as(dp),
+                            t.ctypes.data_as(dp))
+        self.t_update = t[0]
+        return Dx, DhInv, Ddinv
+
+    def condense(self):
+        m = self.meq + self.mineq
+        N = np.zeros((m, m))
+        t = np.zeros(4)
+        lib().ref_qn_condense(self.h, N.ctypes.data_as(dp), t.ctypes.data_as(dp))
+        self.t_condense = t[0]
+        return N
+
+    def solve_compressed(self, rx, ryc, ryd):
+        dx = np.zeros(self.n)
+        dyc = np.zeros(self.meq)
+        dyd = np.zeros(self.mineq)
+        t = np.zeros(4)
+        a = [_d(v) for v in (rx, ryc, ryd)]
+        rc = lib().ref_qn_solve_compressed(self.h, *[p for _, p in a], dx.ctypes.data_as(dp), dyc.ctypes.data_as(dp),
+                                           dyd.ctypes.data_as(dp), t.ctypes.data_as(dp))
+        self.t_solve = t[0]
+        assert rc == 0
+        return dx, dyc, dyd
+
+    def hess_solve(self, rhs):
+        x = np.zeros(self.n)
+        a, pa = _d(rhs)
+        lib().ref_qn_hess_solve(self.h, pa, x.ctypes.data_as(dp))
+        return x
+
+    def hess_times_vec(self, beta, y, alpha, x, add_log_term):
+        yy = np.array(y, dtype=np.float64)
+        a, pa = _d(x)
+        lib().ref_qn_hess_times_vec(self.h, beta, yy.ctypes.data_as(dp), alpha, pa, int(add_log_term))
+        return yy
+
+    def compute_directions(self, res: dict):
+        from .kkt_oracle import RES_NAMES, DIR_NAMES
+        sizes = dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,
+                     sdu=self.mineq, zl=self.n, zu=self.n, vl=self.mineq, vu=self.mineq)
+        rin = [np.ascontiguousarray(res[k], dtype=np.float64) for k in RES_NAMES]
+        dout = [np.zeros(sizes[k]) for k in DIR_NAMES]
+        RA = (dp * 12)(*[a.ctypes.data_as(dp) for a in rin])
+        DA = (dp * 12)(*[a.ctypes.data_as(dp) for a in dout])
+        rc = lib().ref_qn_compute_directions(self.h, RA, DA)
+        assert rc == 0
+        return dict(zip(DIR_NAMES, dout))
+
+
+def symdense_factor_solve(M_upper, rhs=None):
+    """hiopLinSolverSymDenseLapack::matrixChanged (+ solve). Returns (ret, solution or None, factor, times)."""
+    N = M_upper.shape[0]
+    M, pM = _d(M_upper)
+    fac = np.zeros((N, N))
+    t = np.zeros(2)
+    if rhs is None:
+        x = np.zeros(max(N, 1))
+        nrhs = 0
+    else:
+        x = np.array(rhs, dtype=np.float64).reshape(-1, N).copy()
+        nrhs = x.shape[0]
+    ret = lib().ref_symdense_factor_solve(N, pM, nrhs, x.ctypes.data_as(dp), fac.ctypes.data_as(dp), t.ctypes.data_as(dp))
+    sol = None if rhs is None else x.reshape(np.shape(rhs))
+    return ret, sol, fac, t

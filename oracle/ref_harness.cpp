@@ -1,0 +1,439 @@
+// TEST INFRASTRUCTURE ONLY -- never linked into, imported by, or called from the product (hiop_b200/).
+//
+// Flat C wrapper around the UNMODIFIED reference classes compiled into oracle/_ref/libhiop_ref.a
+// (recipe: oracle/Makefile). It lets tests / golden-vector generators / the CPU-baseline leg of bench.py
+// replay one KKT system through the reference's own code on plain host arrays:
+//
+//   ref_qn_*        hiopKKTLinSysLowRank::update + solveCompressed      src/Optimization/hiopKKTLinSys.cpp:1057-1190
+//                   hiopHessianLowRank::{updateLogBarrierDiagonal,solve,symMatTimesInverseTimesMatTrans,timesVec}
+//                                                                        src/Optimization/hiopHessianLowRank.cpp:221-630
+//                   hiopKKTLinSysCompressedXYcYd::computeDirections      src/Optimization/hiopKKTLinSys.cpp:585-691
+//   ref_symdense_*  hiopLinSolverSymDenseLapack::{matrixChanged,solve}   src/LinAlg/hiopLinSolverSymDenseLapack.hpp:75-192
+//   ref_vec_op      hiopVectorPar elementwise ops and reductions         src/LinAlg/hiopVectorPar.cpp
+//   ref_mat_*       hiopMatrixDenseRowMajor / hiopMatrixSparseTriplet assembly ops used by the MDS KKT build
+//
+// Compiled with -fno-access-control because the quasi-Newton state (S_t, Y_t, L, D, sigma) is private in
+// hiopHessianLowRank (hiopHessianLowRank.hpp:128-160) and the residual blocks are private in hiopResidual.
+#include "hiopInterface.hpp"
+#include "hiopNlpFormulation.hpp"
+#include "hiopIterate.hpp"
+#include "hiopResidual.hpp"
+#include "hiopHessianLowRank.hpp"
+#include "hiopKKTLinSys.hpp"
+#include "hiopLinSolverSymDenseLapack.hpp"
+#include "hiopVectorPar.hpp"
+#include "hiopMatrixDenseRowMajor.hpp"
+#include "hiopMatrixSparseTriplet.hpp"
+#include "hiopPDPerturbation.hpp"
+#include "LinAlgFactory.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <vector>
+#include <cmath>
+
+using namespace hiop;
+
+namespace {
+
+/// Synthetic dense-constraints NLP whose only job is to expose sizes and bound patterns to hiopNlpDenseConstraints.
+class SynthDenseCons : public hiopInterfaceDenseConstraints
+{
+public:
+  SynthDenseCons(int n, int m_eq, int m_ineq, const double* ixl, const double* ixu, const double* idl, const double* idu)
+    : n_(n), meq_(m_eq), mineq_(m_ineq), ixl_(ixl, ixl + n), ixu_(ixu, ixu + n), idl_(idl, idl + m_ineq), idu_(idu, idu + m_ineq)
+  {}
+  bool get_prob_sizes(size_type& n, size_type& m) { n = n_; m = meq_ + mineq_; return true; }
+  bool get_vars_info(const size_type& n, double* xlow, double* xupp, NonlinearityType* type)
+  {
+    for(int i = 0; i < n; i++) {
+      xlow[i] = ixl_[i] == 1.0 ? 0.0 : -1e20;
+      xupp[i] = ixu_[i] == 1.0 ? 10.0 : 1e20;
+      type[i] = hiopNonlinear;
+    }
+    return true;
+  }
+  bool get_cons_info(const size_type& m, double* clow, double* cupp, NonlinearityType* type)
+  {
+    for(int i = 0; i < meq_; i++) { clow[i] = cupp[i] = 1.0; type[i] = hiopNonlinear; }
+    for(int i = 0; i < mineq_; i++) {
+      clow[meq_ + i] = idl_[i] == 1.0 ? 0.0 : -1e20;
+      cupp[meq_ + i] = idu_[i] == 1.0 ? 10.0 : 1e20;
+      type[meq_ + i] = hiopNonlinear;
+    }
+    return true;
+  }
+  bool eval_f(const size_type&, const double*, bool, double& f) { f = 0.; return true; }
+  bool eval_grad_f(const size_type& n, const double*, bool, double* g) { memset(g, 0, n * sizeof(double)); return true; }
+  bool eval_cons(const size_type&, const size_type&, const size_type& nc, const index_type*, const double*, bool, double* c)
+  { memset(c, 0, nc * sizeof(double)); return true; }
+  bool eval_Jac_cons(const size_type& n, const size_type&, const size_type& nc, const index_type*, const double*, bool, double* J)
+  { memset(J, 0, sizeof(double) * n * nc); return true; }
+  bool get_vecdistrib_info(size_type, index_type*) { return false; }
+
+private:
+  int n_, meq_, mineq_;
+  std::vector<double> ixl_, ixu_, idl_, idu_;
+};
+
+double now_s()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct QnCtx
+{
+  SynthDenseCons* iface;
+  hiopNlpDenseConstraints* nlp;
+  hiopIterate* it;
+  hiopHessianLowRank* hess;
+  hiopKKTLinSysLowRank* kkt;
+  hiopMatrixDense *Jc, *Jd;
+  hiopVector* gradf;
+  int n, meq, mineq, lmax;
+};
+
+void set_vec(hiopVector* v, const double* src) { if(v->get_size() > 0) memcpy(v->local_data(), src, sizeof(double) * v->get_size()); }
+void get_vec(const hiopVector* v, double* dst) { if(v->get_size() > 0) memcpy(dst, v->local_data_const(), sizeof(double) * v->get_size()); }
+
+} // namespace
+
+extern "C" {
+
+void* ref_qn_create(int n, int m_eq, int m_ineq, int lmax, const double* ixl, const double* ixu, const double* idl, const double* idu)
+{
+  QnCtx* c = new QnCtx;
+  c->n = n; c->meq = m_eq; c->mineq = m_ineq; c->lmax = lmax;
+  c->iface = new SynthDenseCons(n, m_eq, m_ineq, ixl, ixu, idl, idu);
+  c->nlp = new hiopNlpDenseConstraints(*c->iface);
+  c->nlp->options->SetIntegerValue("verbosity_level", 0);
+  c->nlp->options->SetIntegerValue("secant_memory_len", lmax);
+  c->nlp->options->SetStringValue("fixed_var", "relax");
+  c->nlp->finalizeInitialization();
+  c->it = new hiopIterate(c->nlp);
+  c->hess = new hiopHessianLowRank(c->nlp, lmax);
+  c->kkt = new hiopKKTLinSysLowRank(c->nlp);
+  c->Jc = c->nlp->alloc_Jac_c();
+  c->Jd = c->nlp->alloc_Jac_d();
+  c->gradf = c->nlp->alloc_primal_vec();
+  c->gradf->setToZero();
+  return c;
+}
+
+void ref_qn_destroy(void* h)
+{
+  QnCtx* c = (QnCtx*)h;
+  delete c->gradf; delete c->Jd; delete c->Jc; delete c->kkt; delete c->hess; delete c->it; delete c->nlp; delete c->iface;
+  delete c;
+}
+
+/// sizes as the formulation sees them (sanity check for the eq/ineq split): out = {n, m_eq, m_ineq, n_low, n_upp}
+void ref_qn_sizes(void* h, int* out)
+{
+  QnCtx* c = (QnCtx*)h;
+  out[0] = c->nlp->n(); out[1] = c->nlp->m_eq(); out[2] = c->nlp->m_ineq();
+  out[3] = c->nlp->n_low_local(); out[4] = c->nlp->n_upp_local();
+}
+
+void ref_qn_set_iterate(void* h, const double* sxl, const double* sxu, const double* zl, const double* zu,
+                        const double* sdl, const double* sdu, const double* vl, const double* vu)
+{
+  QnCtx* c = (QnCtx*)h;
+  set_vec(c->it->sxl, sxl); set_vec(c->it->sxu, sxu); set_vec(c->it->zl, zl); set_vec(c->it->zu, zu);
+  set_vec(c->it->sdl, sdl); set_vec(c->it->sdu, sdu); set_vec(c->it->vl, vl); set_vec(c->it->vu, vu);
+  c->it->x->setToZero(); c->it->d->setToZero(); c->it->yc->setToZero(); c->it->yd->setToZero();
+}
+
+void ref_qn_set_jac(void* h, const double* Jc, const double* Jd)
+{
+  QnCtx* c = (QnCtx*)h;
+  if(c->meq) memcpy(c->Jc->local_data(), Jc, sizeof(double) * (size_t)c->meq * c->n);
+  if(c->mineq) memcpy(c->Jd->local_data(), Jd, sizeof(double) * (size_t)c->mineq * c->n);
+}
+
+/// Plants the compact-BFGS state: S_t,Y_t are l x n row-major, L is l x l (strictly lower = s_i^T y_j), D is l.
+void ref_qn_set_secant(void* h, int l, double sigma, const double* St, const double* Yt, const double* L, const double* D)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopHessianLowRank* H = c->hess;
+  H->alloc_for_limited_mem(l);
+  H->l_curr = l;
+  H->sigma = sigma;
+  if(l > 0) {
+    memcpy(H->St_->local_data(), St, sizeof(double) * (size_t)l * c->n);
+    memcpy(H->Yt_->local_data(), Yt, sizeof(double) * (size_t)l * c->n);
+    memcpy(H->L_->local_data(), L, sizeof(double) * l * l);
+    memcpy(H->D_->local_data(), D, sizeof(double) * l);
+  }
+  H->matrixChanged = true;
+}
+
+/// hiopKKTLinSysLowRank::update -> Dx, DhInv, Dd_inv. times[0] = seconds.
+void ref_qn_update(void* h, double* Dx, double* DhInv, double* Dd_inv, double* times)
+{
+  QnCtx* c = (QnCtx*)h;
+  double t0 = now_s();
+  c->kkt->update(c->it, c->gradf, c->Jc, c->Jd, c->hess);
+  times[0] = now_s() - t0;
+  if(Dx) get_vec(c->kkt->Dx_, Dx);
+  if(DhInv) get_vec(c->hess->DhInv, DhInv);
+  if(Dd_inv) get_vec(c->kkt->Dd_inv_, Dd_inv);
+}
+
+/// N = J (B+Dx)^{-1} J^T + blkdiag(0, Dd_inv), as formed at hiopKKTLinSys.cpp:1124-1135. Nout is m x m row-major.
+void ref_qn_condense(void* h, double* Nout, double* times)
+{
+  QnCtx* c = (QnCtx*)h;
+  int m = c->meq + c->mineq;
+  hiopMatrixDense* J = c->nlp->alloc_multivector_primal(m);
+  hiopMatrixDense* N = LinearAlgebraFactory::create_matrix_dense("DEFAULT", m, m);
+  double t0 = now_s();
+  J->copyRowsFrom(*c->Jc, c->meq, 0);
+  J->copyRowsFrom(*c->Jd, c->mineq, c->meq);
+  c->hess->symMatTimesInverseTimesMatTrans(0.0, *N, 1.0, *J);
+  N->addSubDiagonal(1., c->meq, *c->kkt->Dd_inv_);
+  times[0] = now_s() - t0;
+  memcpy(Nout, N->local_data(), sizeof(double) * (size_t)m * m);
+  delete N; delete J;
+}
+
+/// hiopKKTLinSysLowRank::solveCompressed. rx is clobbered by the reference (hiopKKTLinSys.cpp:1178); we pass a copy.
+int ref_qn_solve_compressed(void* h, const double* rx, const double* ryc, const double* ryd,
+                            double* dx, double* dyc, double* dyd, double* times)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopVector* vrx = c->nlp->alloc_primal_vec(); hiopVector* vdx = c->nlp->alloc_primal_vec();
+  hiopVector* vryc = c->nlp->alloc_dual_eq_vec(); hiopVector* vdyc = c->nlp->alloc_dual_eq_vec();
+  hiopVector* vryd = c->nlp->alloc_dual_ineq_vec(); hiopVector* vdyd = c->nlp->alloc_dual_ineq_vec();
+  set_vec(vrx, rx); set_vec(vryc, ryc); set_vec(vryd, ryd);
+  double t0 = now_s();
+  bool ok = c->kkt->solveCompressed(*vrx, *vryc, *vryd, *vdx, *vdyc, *vdyd);
+  times[0] = now_s() - t0;
+  get_vec(vdx, dx); get_vec(vdyc, dyc); get_vec(vdyd, dyd);
+  delete vrx; delete vdx; delete vryc; delete vdyc; delete vryd; delete vdyd;
+  return ok ? 0 : -1;
+}
+
+/// hiopHessianLowRank::solve: x = (B_k + D_x)^{-1} rhs
+void ref_qn_hess_solve(void* h, const double* rhs, double* x)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopVector* r = c->nlp->alloc_primal_vec(); hiopVector* xx = c->nlp->alloc_primal_vec();
+  set_vec(r, rhs);
+  c->hess->solve(*r, *xx);
+  get_vec(xx, x);
+  delete r; delete xx;
+}
+
+/// hiopHessianLowRank::timesVec (recursive BFGS product; addLogTerm as used by the full-KKT operator)
+void ref_qn_hess_times_vec(void* h, double beta, double* y, double alpha, const double* x, int add_log_term)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopVector* vy = c->nlp->alloc_primal_vec(); hiopVector* vx = c->nlp->alloc_primal_vec();
+  set_vec(vy, y); set_vec(vx, x);
+  c->hess->timesVecCmn(beta, *vy, alpha, *vx, add_log_term != 0);
+  get_vec(vy, y);
+  delete vy; delete vx;
+}
+
+/// hiopKKTLinSysCompressedXYcYd::computeDirections on the 12 residual blocks -> 12 direction blocks.
+/// res/dir order: x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu  (n, mi, me, mi, n, n, mi, mi, n, n, mi, mi)
+/// residual order: rx, rd, ryc, ryd, rxl, rxu, rdl, rdu, rszl, rszu, rsvl, rsvu
+int ref_qn_compute_directions(void* h, const double* const* res, double* const* dir)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopResidual r(c->nlp);
+  hiopIterate d(c->nlp);
+  set_vec(r.rx, res[0]); set_vec(r.rd, res[1]); set_vec(r.ryc, res[2]); set_vec(r.ryd, res[3]);
+  set_vec(r.rxl, res[4]); set_vec(r.rxu, res[5]); set_vec(r.rdl, res[6]); set_vec(r.rdu, res[7]);
+  set_vec(r.rszl, res[8]); set_vec(r.rszu, res[9]); set_vec(r.rsvl, res[10]); set_vec(r.rsvu, res[11]);
+  bool ok = c->kkt->computeDirections(&r, &d);
+  get_vec(d.x, dir[0]); get_vec(d.d, dir[1]); get_vec(d.yc, dir[2]); get_vec(d.yd, dir[3]);
+  get_vec(d.sxl, dir[4]); get_vec(d.sxu, dir[5]); get_vec(d.sdl, dir[6]); get_vec(d.sdu, dir[7]);
+  get_vec(d.zl, dir[8]); get_vec(d.zu, dir[9]); get_vec(d.vl, dir[10]); get_vec(d.vu, dir[11]);
+  return ok ? 0 : -1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hiopLinSolverSymDenseLapack (B1). M is N x N row-major with the UPPER triangle valid (hiopKKTLinSysMDS.cpp:196-206).
+// Returns matrixChanged()'s value: #negative eigenvalues, or -1 when singular. rhs (nrhs vectors) solved in place.
+// ---------------------------------------------------------------------------------------------------------
+int ref_symdense_factor_solve(int N, const double* M, int nrhs, double* rhs, double* factor_out, double* times)
+{
+  static const double one = 1.0;
+  SynthDenseCons iface(1, 0, 0, &one, &one, &one, &one);
+  hiopNlpDenseConstraints nlp(iface);
+  nlp.options->SetIntegerValue("verbosity_level", 0);
+  hiopLinSolverSymDenseLapack ls(N, &nlp);
+  memcpy(ls.sysMatrix().local_data(), M, sizeof(double) * (size_t)N * N);
+  double t0 = now_s();
+  int ret = ls.matrixChanged();
+  if(times) times[0] = now_s() - t0;
+  if(factor_out) memcpy(factor_out, ls.sysMatrix().local_data(), sizeof(double) * (size_t)N * N);
+  t0 = now_s();
+  if(ret >= 0 || ret == -1) {
+    for(int k = 0; k < nrhs; k++) {
+      hiopVectorPar x(N);
+      memcpy(x.local_data(), rhs + (size_t)k * N, sizeof(double) * N);
+      bool ok = ls.solve(x);
+      (void)ok;
+      memcpy(rhs + (size_t)k * N, x.local_data(), sizeof(double) * N);
+    }
+  }
+  if(times) times[1] = now_s() - t0;
+  return ret;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hiopVectorPar ops. y is in/out; returns the scalar result for reductions (0 otherwise).
+// ---------------------------------------------------------------------------------------------------------
+enum {
+  OP_AXDZPY_W_PATTERN = 1,   // y += alpha*x/z where sel==1            hiopVectorPar.cpp:767-790
+  OP_AXZPY = 2,              // y += alpha*x*z                          :710-734
+  OP_AXDZPY = 3,             // y += alpha*x/z                          :736-765
+  OP_COMPONENT_MULT = 4,     // y *= x                                  :564-572
+  OP_COMPONENT_DIV = 5,      // y /= x                                  :574-582
+  OP_COMPONENT_DIV_W_SEL = 6,// y = sel ? y/x : 0                       :584-592
+  OP_INVERT = 7,             // y = 1/y                                 :852-860
+  OP_SELECT_PATTERN = 8,     // y = sel ? y : 0                         :1063-1071
+  OP_ADD_CONSTANT = 9,       // y += alpha                              :793-797
+  OP_ADD_CONSTANT_W_SEL = 10,// y += alpha where sel==1                 :799-804
+  OP_SCALE = 11,             // y *= alpha
+  OP_AXPY = 12,              // y += alpha*x
+  OP_ADD_LOGBAR_GRAD = 13,   // y += alpha/x where sel==1               :893-905
+  OP_ADD_LIN_DAMPING = 14,   // y = alpha*y + beta*(ixl-ixu)  (x=ixl,z=ixu)   :927-944
+  OP_TWONORM = 20, OP_DOT = 21, OP_INFNORM = 22, OP_ONENORM = 23,
+  OP_LOGBARRIER = 24,        // sum log(y_i) where sel==1 (Kahan)       :863-881
+  OP_LIN_DAMPING_TERM = 25,  // sum y_i where x(ixl)==1 && z(ixu)==0, times alpha(mu)*beta(kappa_d)  :907-925
+  OP_MIN_W_PATTERN = 26,     // min y_i where sel==1                    :821-839
+  OP_FRAC_TO_BDRY = 27,      // fractionToTheBdry_local(y=x, x=dx, alpha=tau)            :1017-1036
+  OP_FRAC_TO_BDRY_W_SEL = 28,// fractionToTheBdry_w_pattern_local(y=x, x=dx, alpha=tau, sel)  :1038-1061
+  OP_SUM = 29,
+};
+
+double ref_vec_op(int op, int n, double* y, const double* x, const double* z, const double* sel, double alpha, double beta)
+{
+  hiopVectorPar vy(n), vx(n), vz(n), vs(n);
+  if(n > 0) {
+    memcpy(vy.local_data(), y, sizeof(double) * n);
+    if(x) memcpy(vx.local_data(), x, sizeof(double) * n);
+    if(z) memcpy(vz.local_data(), z, sizeof(double) * n);
+    if(sel) memcpy(vs.local_data(), sel, sizeof(double) * n);
+  }
+  double ret = 0.;
+  switch(op) {
+    case OP_AXDZPY_W_PATTERN: vy.axdzpy_w_pattern(alpha, vx, vz, vs); break;
+    case OP_AXZPY: vy.axzpy(alpha, vx, vz); break;
+    case OP_AXDZPY: vy.axdzpy(alpha, vx, vz); break;
+    case OP_COMPONENT_MULT: vy.componentMult(vx); break;
+    case OP_COMPONENT_DIV: vy.componentDiv(vx); break;
+    case OP_COMPONENT_DIV_W_SEL: vy.componentDiv_w_selectPattern(vx, vs); break;
+    case OP_INVERT: vy.invert(); break;
+    case OP_SELECT_PATTERN: vy.selectPattern(vs); break;
+    case OP_ADD_CONSTANT: vy.addConstant(alpha); break;
+    case OP_ADD_CONSTANT_W_SEL: vy.addConstant_w_patternSelect(alpha, vs); break;
+    case OP_SCALE: vy.scale(alpha); break;
+    case OP_AXPY: vy.axpy(alpha, vx); break;
+    case OP_ADD_LOGBAR_GRAD: vy.addLogBarrierGrad(alpha, vx, vs); break;
+    case OP_ADD_LIN_DAMPING: vy.addLinearDampingTerm(vx, vz, alpha, beta); break;
+    case OP_TWONORM: ret = vy.twonorm(); break;
+    case OP_DOT: ret = vy.dotProductWith(vx); break;
+    case OP_INFNORM: ret = vy.infnorm(); break;
+    case OP_ONENORM: ret = vy.onenorm(); break;
+    case OP_LOGBARRIER: ret = vy.logBarrier_local(vs); break;
+    case OP_LIN_DAMPING_TERM: ret = vy.linearDampingTerm_local(vx, vz, alpha, beta); break;
+    case OP_MIN_W_PATTERN: ret = vy.min_w_pattern(vs); break;
+    case OP_FRAC_TO_BDRY: ret = vy.fractionToTheBdry_local(vx, alpha); break;
+    case OP_FRAC_TO_BDRY_W_SEL: ret = vy.fractionToTheBdry_w_pattern_local(vx, alpha, vs); break;
+    case OP_SUM: ret = vy.sum_local(); break;
+    default: return NAN;
+  }
+  if(n > 0) memcpy(y, vy.local_data(), sizeof(double) * n);
+  return ret;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hiopMatrixDenseRowMajor ops used on the path (a13/a14)
+// ---------------------------------------------------------------------------------------------------------
+/// y = beta*y + alpha*A*x, A m x n row-major                                  hiopMatrixDenseRowMajor.cpp:436-470
+void ref_mat_times_vec(int m, int n, const double* A, double beta, double* y, double alpha, const double* x)
+{
+  hiopMatrixDenseRowMajor M(m, n);
+  memcpy(M.local_data(), A, sizeof(double) * (size_t)m * n);
+  hiopVectorPar vy(m), vx(n);
+  memcpy(vy.local_data(), y, sizeof(double) * m); memcpy(vx.local_data(), x, sizeof(double) * n);
+  M.timesVec(beta, vy, alpha, vx);
+  memcpy(y, vy.local_data(), sizeof(double) * m);
+}
+/// y = beta*y + alpha*A^T*x                                                   :494-528
+void ref_mat_trans_times_vec(int m, int n, const double* A, double beta, double* y, double alpha, const double* x)
+{
+  hiopMatrixDenseRowMajor M(m, n);
+  memcpy(M.local_data(), A, sizeof(double) * (size_t)m * n);
+  hiopVectorPar vy(n), vx(m);
+  memcpy(vy.local_data(), y, sizeof(double) * n); memcpy(vx.local_data(), x, sizeof(double) * m);
+  M.transTimesVec(beta, vy, alpha, vx);
+  memcpy(y, vy.local_data(), sizeof(double) * n);
+}
+/// W(Nw x Nw, upper) block starting (row_start, col_start) += alpha * A^T, A m x n      :779-798
+void ref_mat_trans_add_to_sym_upper(int m, int n, const double* A, int row_start, int col_start, double alpha, int Nw, double* W)
+{
+  hiopMatrixDenseRowMajor M(m, n), Wm(Nw, Nw);
+  memcpy(M.local_data(), A, sizeof(double) * (size_t)m * n);
+  memcpy(Wm.local_data(), W, sizeof(double) * (size_t)Nw * Nw);
+  M.transAddToSymDenseMatrixUpperTriangle(row_start, col_start, alpha, Wm);
+  memcpy(W, Wm.local_data(), sizeof(double) * (size_t)Nw * Nw);
+}
+/// W's diagonal block starting at diag_start += alpha * triu(A), A n x n                   :810-829
+void ref_mat_add_upper_to_sym_upper(int n, const double* A, int diag_start, double alpha, int Nw, double* W)
+{
+  hiopMatrixDenseRowMajor M(n, n), Wm(Nw, Nw);
+  memcpy(M.local_data(), A, sizeof(double) * (size_t)n * n);
+  memcpy(Wm.local_data(), W, sizeof(double) * (size_t)Nw * Nw);
+  M.addUpperTriangleToSymDenseMatrixUpperTriangle(diag_start, alpha, Wm);
+  memcpy(W, Wm.local_data(), sizeof(double) * (size_t)Nw * Nw);
+}
+/// W[start+i, start+i] += alpha*d[i]                                                        :719-737
+void ref_mat_add_sub_diagonal(int Nw, double* W, int start, double alpha, int nd, const double* d)
+{
+  hiopMatrixDenseRowMajor Wm(Nw, Nw);
+  memcpy(Wm.local_data(), W, sizeof(double) * (size_t)Nw * Nw);
+  hiopVectorPar vd(nd);
+  memcpy(vd.local_data(), d, sizeof(double) * nd);
+  Wm.addSubDiagonal(alpha, start, vd);
+  memcpy(W, Wm.local_data(), sizeof(double) * (size_t)Nw * Nw);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// hiopMatrixSparseTriplet Schur terms of the MDS KKT build (a14)
+// ---------------------------------------------------------------------------------------------------------
+/// W diag block at (start,start) += alpha * M * D^{-1} * M^T (upper triangle only)     hiopMatrixSparseTriplet.cpp:390-441
+void ref_sp_add_MDinvMtrans(int m, int n, int nnz, const int* iRow, const int* jCol, const double* vals,
+                            int start, double alpha, const double* D, int Nw, double* W)
+{
+  hiopMatrixSparseTriplet M(m, n, nnz);
+  memcpy(M.i_row(), iRow, sizeof(int) * nnz); memcpy(M.j_col(), jCol, sizeof(int) * nnz); memcpy(M.M(), vals, sizeof(double) * nnz);
+  hiopMatrixDenseRowMajor Wm(Nw, Nw);
+  memcpy(Wm.local_data(), W, sizeof(double) * (size_t)Nw * Nw);
+  hiopVectorPar vd(n);
+  memcpy(vd.local_data(), D, sizeof(double) * n);
+  M.addMDinvMtransToDiagBlockOfSymDeMatUTri(start, alpha, vd, Wm);
+  memcpy(W, Wm.local_data(), sizeof(double) * (size_t)Nw * Nw);
+}
+/// W block at (row_start,col_start) += alpha * M1 * D^{-1} * M2^T                        :447-525
+void ref_sp_add_MDinvNtrans(int m1, int n, int nnz1, const int* iRow1, const int* jCol1, const double* vals1,
+                            int m2, int nnz2, const int* iRow2, const int* jCol2, const double* vals2,
+                            int row_start, int col_start, double alpha, const double* D, int Nw, double* W)
+{
+  hiopMatrixSparseTriplet M1(m1, n, nnz1), M2(m2, n, nnz2);
+  memcpy(M1.i_row(), iRow1, sizeof(int) * nnz1); memcpy(M1.j_col(), jCol1, sizeof(int) * nnz1); memcpy(M1.M(), vals1, sizeof(double) * nnz1);
+  memcpy(M2.i_row(), iRow2, sizeof(int) * nnz2); memcpy(M2.j_col(), jCol2, sizeof(int) * nnz2); memcpy(M2.M(), vals2, sizeof(double) * nnz2);
+  hiopMatrixDenseRowMajor Wm(Nw, Nw);
+  memcpy(Wm.local_data(), W, sizeof(double) * (size_t)Nw * Nw);
+  hiopVectorPar vd(n);
+  memcpy(vd.local_data(), D, sizeof(double) * n);
+  M1.addMDinvNtransToSymDeMatUTri(row_start, col_start, alpha, vd, M2, Wm);
+  memcpy(W, Wm.local_data(), sizeof(double) * (size_t)Nw * Nw);
+}
+
+} // extern "C"
