@@ -162,21 +162,22 @@ extern "C" int hb_vec_axpy(hb_ctx* c, long long n, double* y, double alpha, cons
 }
 extern "C" int hb_vec_axzpy(hb_ctx* c, long long n, double* y, double alpha, const double* x, const double* z)
 {
-  // the reference special-cases alpha = +-1 only to skip a multiply (hiopVectorPar.cpp:720-733); alpha*x*z keeps its order
-  return ew(c, n, y, x, z, nullptr, [alpha] __device__(double y, double x, double z, double) { return y + alpha * x * z; });
+  // the reference special-cases alpha = +-1 only to skip a multiply (hiopVectorPar.cpp:720-733); (alpha*x)*z then +y, each
+  // rounded separately (no FMA contraction) so the result is bit-identical to the CPU path
+  return ew(c, n, y, x, z, nullptr, [alpha] __device__(double y, double x, double z, double) { return __dadd_rn(y, __dmul_rn(__dmul_rn(alpha, x), z)); });
 }
 extern "C" int hb_vec_axdzpy(hb_ctx* c, long long n, double* y, double alpha, const double* x, const double* z)
 {
   // reference order for general alpha: x/z*alpha (hiopVectorPar.cpp:761)
-  return ew(c, n, y, x, z, nullptr, [alpha] __device__(double y, double x, double z, double) { return y + x / z * alpha; });
+  return ew(c, n, y, x, z, nullptr, [alpha] __device__(double y, double x, double z, double) { return __dadd_rn(y, __dmul_rn(__ddiv_rn(x, z), alpha)); });
 }
 extern "C" int hb_vec_axdzpy_w_pattern(hb_ctx* c, long long n, double* y, double alpha, const double* x, const double* z,
                                        const double* sel)
 {
-  HB_REQUIRE(sel, "axdzpy_w_pattern: null pattern");
+  HB_REQUIRE(sel || n == 0, "axdzpy_w_pattern: null pattern");
   // masked-out lanes may hold z == 0 (tests/LinAlg/vectorTests.hpp:1187-1191): the division is not evaluated there
   return ew(c, n, y, x, z, sel,
-            [alpha] __device__(double y, double x, double z, double s) { return s == 1.0 ? y + alpha * x / z : y; });
+            [alpha] __device__(double y, double x, double z, double s) { return s == 1.0 ? __dadd_rn(y, __ddiv_rn(__dmul_rn(alpha, x), z)) : y; });
 }
 extern "C" int hb_vec_component_mult(hb_ctx* c, long long n, double* y, const double* x)
 {
@@ -188,7 +189,7 @@ extern "C" int hb_vec_component_div(hb_ctx* c, long long n, double* y, const dou
 }
 extern "C" int hb_vec_component_div_w_pattern(hb_ctx* c, long long n, double* y, const double* x, const double* sel)
 {
-  HB_REQUIRE(sel, "component_div_w_pattern: null pattern");
+  HB_REQUIRE(sel || n == 0, "component_div_w_pattern: null pattern");
   // masked-out entries are set to 0, not kept (hiopVectorPar.cpp:588-591)
   return ew(c, n, y, x, nullptr, sel, [] __device__(double y, double x, double, double s) { return s == 0.0 ? 0.0 : y / x; });
 }
@@ -198,7 +199,7 @@ extern "C" int hb_vec_invert(hb_ctx* c, long long n, double* y)
 }
 extern "C" int hb_vec_select_pattern(hb_ctx* c, long long n, double* y, const double* sel)
 {
-  HB_REQUIRE(sel, "select_pattern: null pattern");
+  HB_REQUIRE(sel || n == 0, "select_pattern: null pattern");
   return ew(c, n, y, nullptr, nullptr, sel, [] __device__(double y, double, double, double s) { return s == 0.0 ? 0.0 : y; });
 }
 extern "C" int hb_vec_add_constant(hb_ctx* c, long long n, double* y, double cst)
@@ -207,19 +208,19 @@ extern "C" int hb_vec_add_constant(hb_ctx* c, long long n, double* y, double cst
 }
 extern "C" int hb_vec_add_constant_w_pattern(hb_ctx* c, long long n, double* y, double cst, const double* sel)
 {
-  HB_REQUIRE(sel, "add_constant_w_pattern: null pattern");
+  HB_REQUIRE(sel || n == 0, "add_constant_w_pattern: null pattern");
   return ew(c, n, y, nullptr, nullptr, sel, [cst] __device__(double y, double, double, double s) { return s == 1.0 ? y + cst : y; });
 }
 extern "C" int hb_vec_add_log_barrier_grad(hb_ctx* c, long long n, double* y, double alpha, const double* x, const double* sel)
 {
-  HB_REQUIRE(sel && x, "add_log_barrier_grad: null argument");
-  return ew(c, n, y, x, nullptr, sel, [alpha] __device__(double y, double x, double, double s) { return s == 1.0 ? y + alpha / x : y; });
+  HB_REQUIRE((sel && x) || n == 0, "add_log_barrier_grad: null argument");
+  return ew(c, n, y, x, nullptr, sel, [alpha] __device__(double y, double x, double, double s) { return s == 1.0 ? __dadd_rn(y, __ddiv_rn(alpha, x)) : y; });
 }
 extern "C" int hb_vec_add_linear_damping_term(hb_ctx* c, long long n, double* y, const double* ixl, const double* ixu, double alpha,
                                               double ct)
 {
-  HB_REQUIRE(ixl && ixu, "add_linear_damping_term: null pattern");
-  return ew(c, n, y, ixl, ixu, nullptr, [alpha, ct] __device__(double y, double l, double u, double) { return alpha * y + ct * (l - u); });
+  HB_REQUIRE((ixl && ixu) || n == 0, "add_linear_damping_term: null pattern");
+  return ew(c, n, y, ixl, ixu, nullptr, [alpha, ct] __device__(double y, double l, double u, double) { return __dadd_rn(__dmul_rn(alpha, y), __dmul_rn(ct, __dsub_rn(l, u))); });
 }
 
 // ---- reductions API --------------------------------------------------------------------------------------------
@@ -243,7 +244,7 @@ extern "C" int hb_vec_onenorm(hb_ctx* c, long long n, const double* x, double* o
 }
 extern "C" int hb_vec_min_w_pattern(hb_ctx* c, long long n, const double* x, const double* sel, double* out)
 {
-  HB_REQUIRE(sel, "min_w_pattern: null pattern");
+  HB_REQUIRE(sel || n == 0, "min_w_pattern: null pattern");
   // the reference starts from 1e100 (hiopVectorPar.cpp:826)
   int rc = reduce<R_MIN>(c, n, x, nullptr, sel, [] __device__(double a, double, double s) { return s == 1.0 ? a : 1e100; }, out);
   if(rc == HB_OK && *out > 1e100) *out = 1e100;
@@ -251,13 +252,13 @@ extern "C" int hb_vec_min_w_pattern(hb_ctx* c, long long n, const double* x, con
 }
 extern "C" int hb_vec_log_barrier(hb_ctx* c, long long n, const double* x, const double* sel, double* out)
 {
-  HB_REQUIRE(sel, "log_barrier: null pattern");
+  HB_REQUIRE(sel || n == 0, "log_barrier: null pattern");
   return reduce<R_SUM>(c, n, x, nullptr, sel, [] __device__(double a, double, double s) { return s != 0.0 ? log(a) : 0.0; }, out);
 }
 extern "C" int hb_vec_linear_damping_term(hb_ctx* c, long long n, const double* x, const double* ixl, const double* ixu, double mu,
                                           double kappa_d, double* out)
 {
-  HB_REQUIRE(ixl && ixu, "linear_damping_term: null pattern");
+  HB_REQUIRE((ixl && ixu) || n == 0, "linear_damping_term: null pattern");
   int rc = reduce<R_SUM>(c, n, x, ixl, ixu, [] __device__(double a, double l, double u) { return (l == 1.0 && u == 0.0) ? a : 0.0; }, out);
   if(rc == HB_OK) {
     double t = *out;
@@ -270,7 +271,7 @@ extern "C" int hb_vec_linear_damping_term(hb_ctx* c, long long n, const double* 
 extern "C" int hb_vec_fraction_to_bdry(hb_ctx* c, long long n, const double* x, const double* dx, double tau, const double* sel,
                                        double* out)
 {
-  HB_REQUIRE(x && dx, "fraction_to_bdry: null argument");
+  HB_REQUIRE((x && dx) || n == 0, "fraction_to_bdry: null argument");
   int rc;
   if(sel)
     rc = reduce<R_MIN>(c, n, x, dx, sel,
