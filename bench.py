@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py -- KKT systems/sec (assemble + factor + solve) on the synthetic NlpDenseConsEx2 generalisation.
+
+One "step" = one complete condensed KKT system of HiOp's quasi-Newton path, exactly the work of
+hiopKKTLinSysLowRank::update + solveCompressed (src/Optimization/hiopKKTLinSys.cpp:1057-1190):
+   D_x / DhInv build -> V (compact BFGS inner matrix) -> N = J (B_k+D_x)^{-1} J^T + D_d^{-1}  (one FP64 DMMA pass over J)
+   -> equilibrated Cholesky of N -> rhs = J H^{-1} rx - [ryc;ryd] -> solve with residual refinement -> dx, dyc, dyd.
+Nothing is cached across steps (the factor is recomputed every step like the reference does).
+
+Workload (BASELINE.json configs[1]): n = 1e6, m = 1000 (500 eq + 500 ineq), l = 6, FP64, synthetic data of the
+distributions in SURVEY.md 8(d). At N GPUs the n (column) dimension is sharded like the reference's MPI layout and the
+condensed (m+2l)^2 block is all-reduced with NCCL: strong scaling (total work fixed).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's engine (one rank per GPU under torchrun)
+  python bench.py --impl reference [...]                          the reference's own CPU path (oracle/_ref) on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_FULL, M_FULL, L_MEM = 1_000_000, 1000, 6
+METRIC = "KKT systems/sec (assemble+factor+solve)"
+UNIT = "systems/s"
+FP64_DMMA_PEAK_TFLOPS = 37.15   # measured on this pool's B200 with tools/microbench_fp64.cu (profiles/microbench_fp64_r01.txt)
+
+
+def flops_syrk(n, Ma):
+    """algorithmic flops of the condensation: n*Ma*(Ma+1) (mul+add on the upper triangle incl. diagonal), SURVEY 8(d)"""
+    return float(n) * Ma * (Ma + 1)
+
+
+def algorithmic_bytes(n, m, l):
+    """ideal bytes of one system, SURVEY 8(d)"""
+    return 8.0 * (3.0 * m * n + 6.0 * l * n + 10.0 * n) + 8.0 * (3.0 * m * m + 4.0 * l * m)
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# reference / CPU arm
+# -----------------------------------------------------------------------------------------------------------------
+def cpu_system_time(n_sample: int, m: int, l: int, repeat: int = 1):
+    """Times the reference's update + solveCompressed on an n_sample-column slice of the workload.
+    Returns (seconds per system at n_sample, kind)."""
+    from hiop_b200 import synth
+    P = synth.make_qn_problem(n_sample, m, l, seed=1234)
+    try:
+        from oracle import ref
+        use_ref = ref.available()
+        if use_ref:
+            ref.lib()
+    except Exception:
+        use_ref = False
+    ts = []
+    if use_ref:
+        q = ref.RefQn(P.n, P.m_eq, P.m_ineq, max(l, 1), P.ixl, P.ixu, P.idl, P.idu)
+        q.set_jac(P.Jc, P.Jd)
+        q.set_secant(P.sigma, P.St, P.Yt, P.L, P.D)
+        for _ in range(repeat):
+            q.set_iterate(P.sxl, P.sxu, P.zl, P.zu, P.sdl, P.sdu, P.vl, P.vu)
+            t0 = time.perf_counter()
+            q.update()
+            q.solve_compressed(P.rx, P.ryc, P.ryd)
+            ts.append(time.perf_counter() - t0)
+        q.close()
+        return min(ts), "reference"
+    from oracle import kkt_oracle as ko
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P.zl, P.sxl, P.zu, P.sxu, P.ixl, P.ixu, P.vl, P.sdl, P.vu, P.sdu, P.idl, P.idu, P.sigma)
+        st = ko.QnState(P.Jc, P.Jd, DhInv, Dd_inv, P.St, P.Yt, P.L, P.D, P.sigma)
+        ko.solve_compressed(st, P.rx, P.ryc, P.ryd)
+        ts.append(time.perf_counter() - t0)
+    return min(ts), "port"
+
+
+def cpu_extrapolate(n1: int, n2: int):
+    """Two sampled sizes -> t(n) = a + b*n (a: the m^3 factor/solve part, b: the n-linear condensation + gemv part);
+    returns (t(N_FULL), t1, t2, kind)."""
+    t1, kind = cpu_system_time(n1, M_FULL, L_MEM)
+    t2, kind = cpu_system_time(n2, M_FULL, L_MEM)
+    b = max((t2 - t1) / (n2 - n1), 0.0)
+    a = max(t1 - b * n1, 0.0)
+    return a + b * N_FULL, t1, t2, kind
+
+
+def cpu_baseline(n_sample: int):
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    t_full, t1, t2, kind = cpu_extrapolate(n_sample // 2, n_sample)
+    return {"value": 1.0 / t_full, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"the reference's update+solveCompressed on {n_sample // 2} and {n_sample} of {N_FULL} columns (all m={M_FULL} rows, "
+                      f"l={L_MEM}): {t1:.2f} s and {t2:.2f} s measured, extrapolated as a + b*n to n={N_FULL} (the condensation triple "
+                      f"loop, >95% of the time, is single-threaded in the reference; BLAS/LAPACK parts use {cores} OpenBLAS threads)",
+            "seconds_full_extrapolated": t_full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
+    n1, n2 = 1500, 3000      # ~2 s of reference CPU work per step
+    ts = []
+    kind = "reference"
+    for i in range(args.warmup + args.steps):
+        tf, t1, t2, kind = cpu_extrapolate(n1, n2)
+        if i >= args.warmup:
+            ts.append((tf, t1, t2))
+    t_full = sum(t[0] for t in ts) / len(ts)
+    val = 1.0 / t_full
+    sample = (f"each step = the reference's update+solveCompressed on {n1} and {n2} of {N_FULL} columns (m={M_FULL}, l={L_MEM}), "
+              f"extrapolated as a + b*n to the full workload; last step measured {ts[-1][1]:.3f} s and {ts[-1][2]:.3f} s")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic NlpDenseConsEx2 generalisation n={N_FULL} m={M_FULL} l={L_MEM} (quasi-Newton condensed KKT)",
+                       "sampled": True},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# -----------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.idx = device_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, smax, reasons = [], None, set()
+        for r in rows:
+            try:
+                r = [x.strip() for x in r]
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # under load = upper half of the samples
+        sm_sorted = sorted(sm)
+        load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_device_problem(ctx, torch, n_local, n_total, m, l, rank, world, dist):
+    """Synthetic inputs generated directly in HBM (same distributions as hiop_b200.synth; torch RNG)."""
+    dev = ctx.device
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    m_ineq = m // 2
+    m_eq = m - m_ineq
+    T = {}
+    with torch.cuda.stream(ctx.stream):
+        J = torch.empty((m, n_local), dtype=torch.float64, device=dev)
+        rows_per = 50
+        for r0 in range(0, m, rows_per):            # chunked: keeps the transient fp64 RNG buffers small
+            r1 = min(m, r0 + rows_per)
+            J[r0:r1].normal_(0.0, 1.0 / np.sqrt(n_total), generator=g)
+        J[0].fill_(1.0)
+        T["J"] = J
+
+        def U(k):
+            return torch.empty(k, dtype=torch.float64, device=dev).uniform_(1e-3, 1.0, generator=g)
+        T["ixl"] = torch.ones(n_local, dtype=torch.float64, device=dev)
+        T["ixu"] = (torch.rand(n_local, dtype=torch.float64, device=dev, generator=g) < 0.1).to(torch.float64)
+        T["sxl"], T["zl"] = U(n_local), U(n_local)
+        T["sxu"], T["zu"] = U(n_local) * T["ixu"], U(n_local) * T["ixu"]
+        T["rx"] = torch.empty(n_local, dtype=torch.float64, device=dev).normal_(generator=g)
+        St = torch.empty((l, n_local), dtype=torch.float64, device=dev).normal_(generator=g)
+        Yt = St * torch.empty((l, n_local), dtype=torch.float64, device=dev).uniform_(0.5, 2.0, generator=g)
+        T["St"], T["Yt"] = St, Yt
+        # replicated (m-sized) data: same seed on every rank
+        g2 = torch.Generator(device=dev)
+        g2.manual_seed(99)
+
+        def U2(k):
+            return torch.empty(k, dtype=torch.float64, device=dev).uniform_(1e-3, 1.0, generator=g2)
+        T["idl"] = torch.ones(m_ineq, dtype=torch.float64, device=dev)
+        T["idu"] = (torch.rand(m_ineq, dtype=torch.float64, device=dev, generator=g2) < 0.1).to(torch.float64)
+        T["sdl"], T["vl"] = U2(m_ineq), U2(m_ineq)
+        T["sdu"], T["vu"] = U2(m_ineq) * T["idu"], U2(m_ineq) * T["idu"]
+        T["ryc"] = torch.empty(m_eq, dtype=torch.float64, device=dev).normal_(generator=g2)
+        T["ryd"] = torch.empty(m_ineq, dtype=torch.float64, device=dev).normal_(generator=g2)
+        SY = St @ Yt.T                               # input generation only (L, D of the secant state)
+        if world > 1:
+            dist.all_reduce(SY)
+        SY = SY.cpu().numpy()
+    ctx.sync()
+    T["L"], T["D"] = np.tril(SY, -1).copy(), np.diag(SY).copy()
+    T["m_eq"], T["m_ineq"] = m_eq, m_ineq
+    return T
+
+
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+    from hiop_b200.engine import Context, KKTLinSysLowRank
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+    ctx = Context(local_rank)
+    if world > 1:
+        uid = [ctx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.init_comm(world, rank, uid[0])
+
+    n, m, l = args.n, args.m, args.l
+    n_local = n // world + (1 if rank < n % world else 0)
+    T = make_device_problem(ctx, torch, n_local, n, m, l, rank, world, dist)
+    m_eq, m_ineq = T["m_eq"], T["m_ineq"]
+    k = KKTLinSysLowRank(ctx, n_local, m_eq, m_ineq, max(l, 1))
+    k.set_patterns(T["ixl"], T["ixu"], T["idl"], T["idu"])
+    k.set_jacobian(T["J"][:m_eq], T["J"][m_eq:])
+    k.set_secant(1.0, T["St"] if l else None, T["Yt"] if l else None, T["L"], T["D"])
+    ctx.enable_timing(True)
+    rx_work = ctx.zeros(n_local)
+    dx, dyc, dyd = ctx.zeros(n_local), ctx.zeros(m_eq), ctx.zeros(m_ineq)
+
+    def step():
+        rx_work.copy_(T["rx"])                        # solveCompressed clobbers rx (like the reference)
+        k.update(T["zl"], T["sxl"], T["zu"], T["sxu"], T["vl"], T["sdl"], T["vu"], T["sdu"])
+        k.condense()
+        ok = k.solveCompressed(rx_work, T["ryc"], T["ryd"], dx, dyc, dyd)
+        assert ok
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        ctx.sync()
+        torch.cuda.synchronize()
+
+    with ctx:                                          # engine stream is torch's current stream: events see the kernels
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        syrk_ms = []
+        e0.record()
+        for _ in range(args.steps):
+            step()
+            syrk_ms.append(ctx.last_syrk_ms())
+        e1.record()
+        barrier()
+        launches = ctx.launch_count() - launches0
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_total], dtype=torch.float64, device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_total = float(t.item())
+        ms_step = ms_total / args.steps
+        nref, resid = k.last_solve_stats()
+
+        # ---- end to end through the host-buffer entry point (public API a HiOp adapter calls when mem_space is host) ----
+        e2e = None
+        if world == 1 and not args.no_e2e:
+            host = {}
+            for key in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu", "rx", "ryc", "ryd"):
+                host[key] = torch.empty(T[key].shape, dtype=torch.float64, pin_memory=True)
+                host[key].copy_(T[key])
+            Jh = torch.empty((m, n_local), dtype=torch.float64, pin_memory=True)
+            Jh.copy_(T["J"])
+            hdx = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+            hyc = torch.empty(m_eq, dtype=torch.float64, pin_memory=True)
+            hyd = torch.empty(m_ineq, dtype=torch.float64, pin_memory=True)
+            ctx.sync()
+            it = {kk: host[kk].numpy() for kk in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu")}
+            Jn = Jh.numpy()
+
+            def e2e_step():
+                k.kkt_system_host(Jn[:m_eq], Jn[m_eq:], it, host["rx"].numpy(), host["ryc"].numpy(), host["ryd"].numpy(),
+                                  hdx.numpy(), hyc.numpy(), hyd.numpy())
+            e2e_step()
+            e2e_steps = max(2, min(args.steps, 5))
+            t0 = time.perf_counter()
+            e0.record()
+            for _ in range(e2e_steps):
+                e2e_step()
+            e1.record()
+            torch.cuda.synchronize()
+            e2e_ms = e0.elapsed_time(e1) / e2e_steps
+            h2d = 8 * (m * n_local + 5 * n_local + 4 * m_ineq + m)
+            d2h = 8 * (n_local + m)
+            e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
+                   "steps": e2e_steps, "note": "hb_lowrank_kkt_system_host: J (8 GB) + iterate + rhs copied from pinned host memory every step"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    Ma = m + 2 * l
+    syrk = statistics.mean(syrk_ms)
+    fl = flops_syrk(n_local, Ma)
+    achieved = fl / (syrk * 1e-3) / 1e12
+    roofline = {"kernel": "k_syrk_diag (FP64 DMMA.8x8x4 condensation [J;S;Y] DhInv [J;S;Y]^T)", "bound": "tensor", "achieved": achieved,
+                "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "kernel_ms": syrk, "kernel_share_of_step": syrk / ms_step,
+                "flops_per_launch": fl,
+                "peak_source": "FP64 tensor (DMMA) peak measured on this pool's B200 by tools/microbench_fp64.cu = 64 FMA/clk/SM x 148 SMs x "
+                               "1965 MHz; MEASURED_PEAKS.json holds only HBM and bf16 numbers (tcgen05 has no f64 kind)",
+                "hbm_algorithmic_GBs_whole_step": algorithmic_bytes(n_local, m, l) / (ms_step * 1e-3) / 1e9}
+    line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"synthetic NlpDenseConsEx2 generalisation n={n} m={m} (m_eq={m_eq}, m_ineq={m_ineq}) l={l}: "
+                                   "quasi-Newton condensed KKT, update+condense+Cholesky+solve every step",
+                       "parallelism": f"column-sharded x{world}" if world > 1 else "single GPU",
+                       "l2": f"J is {8e-9 * m * n_local:.1f} GB per GPU, far larger than the 126 MB L2; no flush needed",
+                       "refinement_steps_last": nref, "residual_inf_last": resid},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.cpu_sample)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--n", type=int, default=N_FULL)
+    ap.add_argument("--m", type=int, default=M_FULL)
+    ap.add_argument("--l", type=int, default=L_MEM)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=20000, help="columns of the workload the CPU baseline leg runs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_engine(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -58,6 +58,8 @@ def lib() -> ctypes.CDLL:
     f("hb_ctx_sync", c_i, c_vp)
     f("hb_ctx_stream", c_vp, c_vp)
     f("hb_ctx_device", c_i, c_vp)
+    f("hb_ctx_enable_timing", c_i, c_vp, c_i)
+    f("hb_ctx_last_syrk_ms", c_i, c_vp, P(ctypes.c_float))
     f("hb_malloc", c_i, c_vp, ctypes.c_size_t, P(c_vp))
     f("hb_free", c_i, c_vp, c_vp)
     f("hb_malloc_host", c_i, c_vp, ctypes.c_size_t, P(c_vp))

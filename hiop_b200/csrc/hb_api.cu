@@ -45,10 +45,31 @@ extern "C" int hb_ctx_destroy(hb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if(c->ws) cudaFree(c->ws);
+  if(c->ev_syrk0) { cudaEventDestroy(c->ev_syrk0); cudaEventDestroy(c->ev_syrk1); }
   cudaFree(c->red_dev);
   cudaFreeHost(c->red_host);
   cudaStreamDestroy(c->stream);
   delete c;
+  return HB_OK;
+}
+
+extern "C" int hb_ctx_enable_timing(hb_ctx* c, int on)
+{
+  HB_REQUIRE(c, "null ctx");
+  if(on && !c->ev_syrk0) {
+    HB_CUDA(cudaEventCreate(&c->ev_syrk0));
+    HB_CUDA(cudaEventCreate(&c->ev_syrk1));
+  }
+  c->timing = on != 0;
+  c->syrk_timed = false;
+  return HB_OK;
+}
+extern "C" int hb_ctx_last_syrk_ms(hb_ctx* c, float* ms)
+{
+  HB_REQUIRE(c && ms, "hb_ctx_last_syrk_ms: null argument");
+  if(!c->timing || !c->syrk_timed) return hb_fail(HB_ERR_STATE, "hb_ctx_last_syrk_ms: no timed SYRK launch recorded%s", "");
+  HB_CUDA(cudaEventSynchronize(c->ev_syrk1));
+  HB_CUDA(cudaEventElapsedTime(ms, c->ev_syrk0, c->ev_syrk1));
   return HB_OK;
 }
 

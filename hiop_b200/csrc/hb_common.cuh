@@ -65,6 +65,10 @@ struct hb_ctx
   // generic workspace (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // optional kernel timing (roofline reporting)
+  bool timing = false;
+  cudaEvent_t ev_syrk0 = nullptr, ev_syrk1 = nullptr;
+  bool syrk_timed = false;
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;

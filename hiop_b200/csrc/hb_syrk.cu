@@ -340,11 +340,16 @@ int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev,
     g_attr_set = true;
   }
   const int G = S.Gl;
+  if(c->timing) HB_CUDA(cudaEventRecord(c->ev_syrk0, c->stream));
   if(aligned16 && ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(rowptr_dev) & 15u) == 0))
     k_syrk_diag<true><<<G, THREADS, SMEM_BYTES, c->stream>>>(rowptr_dev, M, K, d, S.d_segs, S.d_cta_seg_begin, (double*)c->ws);
   else
     k_syrk_diag<false><<<G, THREADS, SMEM_BYTES, c->stream>>>(rowptr_dev, M, K, d, S.d_segs, S.d_cta_seg_begin, (double*)c->ws);
   HB_LAUNCHED();
+  if(c->timing) {
+    HB_CUDA(cudaEventRecord(c->ev_syrk1, c->stream));
+    c->syrk_timed = true;
+  }
   k_syrk_fixup<<<dim3(S.ntiles, BM / 16), 256, 0, c->stream>>>(M, S.d_tile_ij, S.d_tile_slot_begin, S.d_tile_slots, (const double*)c->ws, C, ldc);
   HB_LAUNCHED();
   return HB_OK;

@@ -67,6 +67,14 @@ class Context:
             self.L.hb_ctx_destroy(self.h)
             self.h = None
 
+    def enable_timing(self, on: bool = True):
+        check(self.L.hb_ctx_enable_timing(self.h, int(on)), "hb_ctx_enable_timing")
+
+    def last_syrk_ms(self) -> float:
+        ms = ctypes.c_float()
+        check(self.L.hb_ctx_last_syrk_ms(self.h, ctypes.byref(ms)), "hb_ctx_last_syrk_ms")
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(self.L.hb_launch_count())
 

@@ -54,6 +54,11 @@ int hb_ctx_sync(hb_ctx* ctx);
 void* hb_ctx_stream(hb_ctx* ctx);
 int hb_ctx_device(hb_ctx* ctx);
 
+/* Kernel-level timing for roofline reporting: when enabled, CUDA events bracket the dominant kernel (the FP64 DMMA
+ * condensation SYRK) on the context stream; hb_ctx_last_syrk_ms waits for it and returns its device duration. */
+int hb_ctx_enable_timing(hb_ctx* ctx, int on);
+int hb_ctx_last_syrk_ms(hb_ctx* ctx, float* ms_host);
+
 int hb_malloc(hb_ctx* ctx, size_t bytes, void** dptr);
 int hb_free(hb_ctx* ctx, void* dptr);
 int hb_malloc_host(hb_ctx* ctx, size_t bytes, void** hptr); /* pinned */
