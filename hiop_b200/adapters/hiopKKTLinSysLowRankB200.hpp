@@ -1,0 +1,36 @@
+// hiopKKTLinSysLowRankB200 -- drop-in for hiopKKTLinSysLowRank (src/Optimization/hiopKKTLinSys.hpp:385-460) whose
+// update() / solveCompressed() run on the B200 engine. The rhs reduction and the back-substitution stay in the
+// inherited hiopKKTLinSysCompressedXYcYd::computeDirections (src/Optimization/hiopKKTLinSys.cpp:585-691), i.e. the
+// boundary is exactly the pure-virtual solveCompressed() of the reference (B2 in SURVEY.md section 8b).
+//
+// Needs read access to the compact-BFGS state of hiopHessianLowRank (S_t, Y_t, L, D, sigma are private,
+// src/Optimization/hiopHessianLowRank.hpp:128-160): upstream this is one more `friend class` line next to the existing
+// ones; in this repo the adapter translation unit is compiled with -fno-access-control instead.
+#pragma once
+#include "hiopKKTLinSys.hpp"
+#include "hiopHessianLowRank.hpp"
+#include "hiopb200.h"
+
+namespace hiop
+{
+class hiopKKTLinSysLowRankB200 : public hiopKKTLinSysLowRank
+{
+public:
+  hiopKKTLinSysLowRankB200(hiopNlpFormulation* nlp);
+  virtual ~hiopKKTLinSysLowRankB200();
+
+  bool update(const hiopIterate* iter, const hiopVector* grad_f, const hiopMatrixDense* Jac_c, const hiopMatrixDense* Jac_d,
+              hiopHessianLowRank* Hess) override;
+  bool solveCompressed(hiopVector& rx, hiopVector& ryc, hiopVector& ryd, hiopVector& dx, hiopVector& dyc, hiopVector& dyd) override;
+
+private:
+  bool upload(double* dst, const double* src, size_t count);
+  hb_ctx* ctx_;
+  hb_lowrank* h_;
+  long long n_;
+  int meq_, mineq_, lmax_;
+  // device mirrors
+  double *dJ_, *dSt_, *dYt_;
+  double *dpat_[4], *dit_[8], *drhs_[3], *dsol_[3];
+};
+} // namespace hiop
