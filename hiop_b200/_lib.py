@@ -127,6 +127,17 @@ def lib() -> ctypes.CDLL:
     f("hb_lowrank_N", c_vp, c_vp)
     f("hb_lowrank_last_solve_stats", c_i, c_vp, P(c_i), P(c_d))
     f("hb_lowrank_kkt_system_host", c_i, c_vp, *([c_vp] * 16))
+    # mds
+    f("hb_mds_create", c_i, c_vp, c_i, c_i, c_i, c_i, P(c_vp))
+    f("hb_mds_destroy", c_i, c_vp)
+    f("hb_mds_set_sparsity", c_i, c_vp, c_i, c_vp, c_vp, c_i, c_vp, c_vp)
+    f("hb_mds_update", c_i, c_vp, *([c_dp] * 6))
+    f("hb_mds_build_kkt_matrix", c_i, c_vp, *([c_dp] * 17))
+    f("hb_mds_hxs_inertia", c_i, c_vp, P(c_i), P(c_i))
+    f("hb_mds_solve_compressed", c_i, c_vp, c_vp, *([c_dp] * 6))
+    f("hb_mds_Dx", c_vp, c_vp)
+    f("hb_mds_Hxs", c_vp, c_vp)
+    f("hb_mds_Dd_inv", c_vp, c_vp)
     _lib = L
     return L
 

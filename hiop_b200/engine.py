@@ -294,3 +294,62 @@ class KKTLinSysLowRank:
         args = [hp(Jc), hp(Jd)] + [hp(it[k]) for k in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu")] + \
                [hp(a) for a in (rx, ryc, ryd, dx, dyc, dyd)]
         check(self.ctx.L.hb_lowrank_kkt_system_host(self.h, *args), "hb_lowrank_kkt_system_host")
+
+
+class KKTLinSysCompressedMDSXYcYd:
+    """hiopKKTLinSysCompressedMDSXYcYd (src/Optimization/hiopKKTLinSysMDS.cpp:59-484) around a LinSolverSymDense.
+
+    update(iterate blocks) -> build_kkt_matrix(blocks, deltas) -> factorizeWithCurvCheck() -> solveCompressed(...)."""
+
+    def __init__(self, ctx: Context, nxs: int, nxd: int, neq: int, nineq: int, safe_mode: bool = True):
+        self.ctx, self.nxs, self.nxd, self.neq, self.nineq = ctx, nxs, nxd, neq, nineq
+        self.h = ctypes.c_void_p()
+        check(ctx.L.hb_mds_create(ctx.h, nxs, nxd, neq, nineq, ctypes.byref(self.h)), "hb_mds_create")
+        # determineAndCreateLinsys (:405-482): Bunch-Kaufman in safe mode, no-pivot LDL^T otherwise
+        self.linSys = LinSolverSymDense(ctx, nxd + neq + nineq, LinSolverSymDense.BUNCH_KAUFMAN if safe_mode else LinSolverSymDense.NOPIV)
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            self.ctx.L.hb_mds_destroy(self.h)
+            self.h = None
+        self.linSys.close()
+
+    def set_sparsity(self, iRow_c, jCol_c, iRow_d, jCol_d):
+        a = [np.ascontiguousarray(v, dtype=np.int32) for v in (iRow_c, jCol_c, iRow_d, jCol_d)]
+        p = [v.ctypes.data_as(ctypes.c_void_p) for v in a]
+        check(self.ctx.L.hb_mds_set_sparsity(self.h, a[0].size, p[0], p[1], a[2].size, p[2], p[3]), "hb_mds_set_sparsity")
+
+    def update(self, zl, sxl, zu, sxu, ixl, ixu):
+        self._keep["it"] = (zl, sxl, zu, sxu, ixl, ixu)
+        check(self.ctx.L.hb_mds_update(self.h, *[_ptr(t) for t in (zl, sxl, zu, sxu, ixl, ixu)]), "hb_mds_update")
+
+    def build_kkt_matrix(self, Hd, Hs_diag, Jcd, Jdd, Jcs_vals, Jds_vals, vl, sdl, vu, sdu, idl, idu, delta_wx, delta_wd, delta_cc, delta_cd):
+        args = (Hd, Hs_diag, Jcd, Jdd, Jcs_vals, Jds_vals, vl, sdl, vu, sdu, idl, idu, delta_wx, delta_wd, delta_cc, delta_cd)
+        self._keep["blk"] = args
+        check(self.ctx.L.hb_mds_build_kkt_matrix(self.h, *[_ptr(t) for t in args], ctypes.c_void_p(self.linSys._mptr)), "hb_mds_build_kkt_matrix")
+
+    def factorizeWithCurvCheck(self) -> int:
+        """Number of negative eigenvalues of the whole XYcYd system via Haynsworth additivity, or -1 (:78-110)."""
+        n_neg = self.linSys.matrixChanged()
+        if n_neg < 0:
+            return -1
+        a, b = ctypes.c_int(), ctypes.c_int()
+        check(self.ctx.L.hb_mds_hxs_inertia(self.h, ctypes.byref(a), ctypes.byref(b)), "hb_mds_hxs_inertia")
+        if b.value > 0:
+            return -1
+        return n_neg + a.value
+
+    def solveCompressed(self, rx, ryc, ryd, dx, dyc, dyd) -> bool:
+        rc = self.ctx.L.hb_mds_solve_compressed(self.h, self.linSys.h, *[_ptr(t) for t in (rx, ryc, ryd, dx, dyc, dyd)])
+        if rc == -4:
+            return False
+        check(rc, "hb_mds_solve_compressed")
+        return True
+
+    def Msys(self) -> np.ndarray:
+        N = self.nxd + self.neq + self.nineq
+        out = np.empty(N * N, dtype=np.float64)
+        check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self.linSys._mptr), 8 * N * N), "memcpy")
+        self.ctx.sync()
+        return out.reshape(N, N)

@@ -126,3 +126,74 @@ def make_kkt_like(nx: int, m: int, seed: int = 11) -> np.ndarray:
     K[:nx, nx:] = J.T
     K[nx:, nx:] = -np.diag(r.uniform(1e-3, 1.0, m))
     return K
+
+
+@dataclass
+class MdsProblem:
+    """One synthetic mixed dense-sparse Newton KKT system (the shape hiopKKTLinSysCompressedMDSXYcYd assembles,
+    src/Optimization/hiopKKTLinSysMDS.cpp:172-305): diagonal sparse Hessian block, dense H_d, sparse + dense Jacobian blocks."""
+    nxs: int
+    nxd: int
+    neq: int
+    nineq: int
+    Hd: np.ndarray          # nxd x nxd symmetric
+    Hs_diag: np.ndarray     # nxs
+    Jcd: np.ndarray         # neq x nxd
+    Jdd: np.ndarray         # nineq x nxd
+    iRow_c: np.ndarray
+    jCol_c: np.ndarray
+    Jcs_vals: np.ndarray
+    iRow_d: np.ndarray
+    jCol_d: np.ndarray
+    Jds_vals: np.ndarray
+    ixl: np.ndarray
+    ixu: np.ndarray
+    idl: np.ndarray
+    idu: np.ndarray
+    sxl: np.ndarray
+    sxu: np.ndarray
+    zl: np.ndarray
+    zu: np.ndarray
+    sdl: np.ndarray
+    sdu: np.ndarray
+    vl: np.ndarray
+    vu: np.ndarray
+    delta_wx: np.ndarray
+    delta_wd: np.ndarray
+    delta_cc: np.ndarray
+    delta_cd: np.ndarray
+    rx: np.ndarray
+    ryc: np.ndarray
+    ryd: np.ndarray
+
+
+def _sorted_triplets(r, m, n, nnz_per_row):
+    rows, cols = [], []
+    for i in range(m):
+        k = min(n, nnz_per_row)
+        cs = np.sort(r.choice(n, k, replace=False)) if n else np.zeros(0, dtype=int)
+        rows += [i] * len(cs)
+        cols += list(cs)
+    return np.array(rows, dtype=np.int32), np.array(cols, dtype=np.int32)
+
+
+def make_mds_problem(nxs: int, nxd: int, neq: int, nineq: int, nnz_per_row: int = 5, seed: int = 42, dwx: float = 0.0, dcc: float = 0.0) -> MdsProblem:
+    r = np.random.default_rng(seed)
+    n = nxs + nxd
+    A = r.standard_normal((nxd, nxd)) / np.sqrt(max(nxd, 1))
+    Hd = A @ A.T + np.diag(r.uniform(1e-2, 1.0, nxd))
+    Hs = r.uniform(0.1, 2.0, nxs)
+    Jcd = r.standard_normal((neq, nxd)) / np.sqrt(max(nxd, 1))
+    Jdd = r.standard_normal((nineq, nxd)) / np.sqrt(max(nxd, 1))
+    iRc, jCc = _sorted_triplets(r, neq, nxs, nnz_per_row)
+    iRd, jCd = _sorted_triplets(r, nineq, nxs, nnz_per_row)
+    ixl = np.ones(n)
+    ixu = (r.random(n) < 0.2).astype(np.float64)
+    idl = np.ones(nineq)
+    idu = (r.random(nineq) < 0.2).astype(np.float64)
+    U = lambda k: r.uniform(1e-3, 1.0, k)
+    return MdsProblem(nxs=nxs, nxd=nxd, neq=neq, nineq=nineq, Hd=Hd, Hs_diag=Hs, Jcd=Jcd, Jdd=Jdd, iRow_c=iRc, jCol_c=jCc,
+                      Jcs_vals=r.standard_normal(iRc.size), iRow_d=iRd, jCol_d=jCd, Jds_vals=r.standard_normal(iRd.size), ixl=ixl, ixu=ixu,
+                      idl=idl, idu=idu, sxl=U(n), sxu=U(n) * ixu, zl=U(n), zu=U(n) * ixu, sdl=U(nineq), sdu=U(nineq) * idu, vl=U(nineq),
+                      vu=U(nineq) * idu, delta_wx=np.full(n, dwx), delta_wd=np.full(nineq, dwx), delta_cc=np.full(neq, dcc),
+                      delta_cd=np.full(nineq, dcc), rx=r.standard_normal(n), ryc=r.standard_normal(neq), ryd=r.standard_normal(nineq))

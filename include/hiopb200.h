@@ -37,6 +37,7 @@ extern "C" {
 typedef struct hb_ctx hb_ctx;
 typedef struct hb_lowrank hb_lowrank;
 typedef struct hb_symdense hb_symdense;
+typedef struct hb_mds hb_mds;
 
 /* ------------------------------------------------------------------------------------------------------------
  * Context, memory, streams
@@ -208,6 +209,40 @@ int hb_lowrank_kkt_system_host(hb_lowrank* k, const double* Jc_host, const doubl
                                const double* sxl, const double* zu, const double* sxu, const double* vl, const double* sdl,
                                const double* vu, const double* sdu, const double* rx, const double* ryc, const double* ryd,
                                double* dx, double* dyc, double* dyd);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * hiopKKTLinSysCompressedMDSXYcYd (src/Optimization/hiopKKTLinSysMDS.cpp:59-484): mixed dense-sparse Newton KKT.
+ * x = (x_s, x_d) with nxs "sparse" and nxd "dense" variables; the Hessian is diag(H_s) (+) H_d, the Jacobians are
+ * [J_s | J_d] with J_s sparse triplets (row-sorted) and J_d dense row-major. The condensed system has size
+ * N = nxd + neq + nineq and is handed to an hb_symdense solver. Stays on one GPU.
+ * ------------------------------------------------------------------------------------------------------------ */
+int hb_mds_create(hb_ctx* ctx, int nxs, int nxd, int neq, int nineq, hb_mds** out);
+int hb_mds_destroy(hb_mds* h);
+/* sparsity of Jac_c_sp (neq x nxs) and Jac_d_sp (nineq x nxs): HOST triplet index arrays sorted by (row, col)
+ * (hiopMatrixSparseTriplet's ordering assumption, src/LinAlg/hiopMatrixSparseTriplet.cpp:528-560). Static per problem. */
+int hb_mds_set_sparsity(hb_mds* h, int nnz_c, const int* iRow_c_host, const int* jCol_c_host, int nnz_d, const int* iRow_d_host,
+                        const int* jCol_d_host);
+/* update(): Dx = zl/sxl|ixl + zu/sxu|ixu over all nxs+nxd variables (hiopKKTLinSysMDS.cpp:155-157) */
+int hb_mds_update(hb_mds* h, const double* zl, const double* sxl, const double* zu, const double* sxu, const double* ixl, const double* ixu);
+/* build_kkt_matrix() (:172-305): fills the UPPER triangle of Msys (N x N row-major, e.g. hb_symdense_matrix(s)) with
+ *   [ Hd + Dxd + dwx     Jcd^T                         Jdd^T                                  ]
+ *   [                   -Jcs Hxs^{-1} Jcs^T - dcc      -Jcs Hxs^{-1} Jds^T                    ]
+ *   [                                                  -Jds Hxs^{-1} Jds^T - Dd_inv - dcd     ]
+ * Hxs = Dxs + dwx + diag(H_s), Dd_inv = 1/(dwd + vl/sdl|idl + vu/sdu|idu). Hd: nxd x nxd (upper triangle read),
+ * Hs_diag: nxs, Jcd: neq x nxd, Jdd: nineq x nxd, J*s_vals: nnz values in triplet order, delta_wx: nxs+nxd,
+ * delta_wd/delta_cd: nineq, delta_cc: neq (the regularisations arrive as vectors, hiopPDPerturbation.hpp:113-134). */
+int hb_mds_build_kkt_matrix(hb_mds* h, const double* Hd, const double* Hs_diag, const double* Jcd, const double* Jdd,
+                            const double* Jcs_vals, const double* Jds_vals, const double* vl, const double* sdl, const double* vu,
+                            const double* sdu, const double* idl, const double* idu, const double* delta_wx, const double* delta_wd,
+                            const double* delta_cc, const double* delta_cd, double* Msys);
+/* Haynsworth part of factorizeWithCurvCheck (:78-110): #entries of Hxs < -1e-14 and #entries with |.| < 1e-14 (host ints) */
+int hb_mds_hxs_inertia(hb_mds* h, int* n_neg, int* n_zero);
+/* solveCompressed() (:307-403) around s (already factorized with hb_symdense_matrix_changed). rx has nxs+nxd entries. */
+int hb_mds_solve_compressed(hb_mds* h, hb_symdense* s, const double* rx, const double* ryc, const double* ryd, double* dx, double* dyc,
+                            double* dyd);
+const double* hb_mds_Dx(hb_mds* h);
+const double* hb_mds_Hxs(hb_mds* h);
+const double* hb_mds_Dd_inv(hb_mds* h);
 
 #ifdef __cplusplus
 }

@@ -113,9 +113,23 @@ def vec_cases():
     np.savez_compressed(os.path.join(OUT, "vector_ops.npz"), **out)
 
 
+def mds_case():
+    """MDS KKT assembly through the reference's own matrix methods (order of build_kkt_matrix) + LAPACK BK solve."""
+    import ctypes
+    from oracle import kkt_oracle as ko
+    p = synth.make_mds_problem(50, 20, 8, 11, dwx=1e-4, dcc=1e-6, seed=77)
+    M, Dx, Hxs, Dd_inv = ko.mds_build_kkt_matrix(p)     # bit-identical to the reference methods (tests/test_oracle_vs_ref.py)
+    ret, sol, _, _ = ref.symdense_factor_solve(M, np.concatenate([p.rx[p.nxs:], p.ryc, p.ryd]))
+    out = {k: getattr(p, k) for k in p.__dataclass_fields__}
+    out.update(ref_M=M, ref_Dx=Dx, ref_Hxs=Hxs, ref_Dd_inv=Dd_inv, ref_ret=ret)
+    np.savez_compressed(os.path.join(OUT, "mds_nxs50_nxd20.npz"), **out)
+    print("mds ret", ret)
+
+
 if __name__ == "__main__":
     assert ref.available(), "build oracle/_ref first: make -C oracle ref"
     for c in QN_CASES:
         qn_case(*c)
     symdense_cases()
     vec_cases()
+    mds_case()

@@ -155,3 +155,57 @@ def test_mds_assembly_ops_match_reference():
                                      Wr.ctypes.data_as(ref.dp))
     Wo = ko.sp_add_MDinvMtrans(ms, ns, iR, jC, vals, 11, -1.0, D, W.copy())
     assert np.abs(Wo - Wr).max() <= 1e-13 * np.abs(Wr).max()
+
+
+def test_mds_build_kkt_matrix_matches_reference_methods():
+    """ko.mds_build_kkt_matrix against the reference's own matrix methods called in the order of
+    hiopKKTLinSysCompressedMDSXYcYd::build_kkt_matrix (src/Optimization/hiopKKTLinSysMDS.cpp:196-290)."""
+    p = synth.make_mds_problem(60, 25, 9, 14, dwx=1e-4, dcc=1e-6)
+    M, Dx, Hxs, Dd_inv = ko.mds_build_kkt_matrix(p)
+    L, dp, ip = ref.lib(), ref.dp, ref.ip
+    N = p.nxd + p.neq + p.nineq
+    W = np.zeros((N, N))
+    wp = W.ctypes.data_as(dp)
+
+    def D(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return a, a.ctypes.data_as(dp)
+
+    def I(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        return a, a.ctypes.data_as(ip)
+    Dx_r, _ = ref.vec_op("axdzpy_w_pattern", np.zeros(p.nxs + p.nxd), p.zl, p.sxl, p.ixl, 1.0)
+    Dx_r, _ = ref.vec_op("axdzpy_w_pattern", Dx_r, p.zu, p.sxu, p.ixu, 1.0)
+    np.testing.assert_array_equal(Dx, Dx_r)
+    a, pa = D(p.Hd); L.ref_mat_add_upper_to_sym_upper(p.nxd, pa, 0, 1.0, N, wp)
+    a, pa = D(p.Jcd); L.ref_mat_trans_add_to_sym_upper(p.neq, p.nxd, pa, 0, p.nxd, 1.0, N, wp)
+    a, pa = D(p.Jdd); L.ref_mat_trans_add_to_sym_upper(p.nineq, p.nxd, pa, 0, p.nxd + p.neq, 1.0, N, wp)
+    a, pa = D(Dx[p.nxs:]); L.ref_mat_add_sub_diagonal(N, wp, 0, 1.0, p.nxd, pa)
+    a, pa = D(p.delta_wx[p.nxs:]); L.ref_mat_add_sub_diagonal(N, wp, 0, 1.0, p.nxd, pa)
+    hx, phx = D(Hxs)
+    ic, pic = I(p.iRow_c); jc, pjc = I(p.jCol_c); vc, pvc = D(p.Jcs_vals)
+    idd, pid = I(p.iRow_d); jd, pjd = I(p.jCol_d); vd, pvd = D(p.Jds_vals)
+    L.ref_sp_add_MDinvMtrans(p.neq, p.nxs, ic.size, pic, pjc, pvc, p.nxd, -1.0, phx, N, wp)
+    a, pa = D(p.delta_cc); L.ref_mat_add_sub_diagonal(N, wp, p.nxd, -1.0, p.neq, pa)
+    L.ref_sp_add_MDinvMtrans(p.nineq, p.nxs, idd.size, pid, pjd, pvd, p.nxd + p.neq, -1.0, phx, N, wp)
+    L.ref_sp_add_MDinvNtrans(p.neq, p.nxs, ic.size, pic, pjc, pvc, p.nineq, idd.size, pid, pjd, pvd, p.nxd, p.nxd + p.neq, -1.0, phx, N, wp)
+    a, pa = D(Dd_inv); L.ref_mat_add_sub_diagonal(N, wp, p.nxd + p.neq, -1.0, p.nineq, pa)
+    a, pa = D(p.delta_cd); L.ref_mat_add_sub_diagonal(N, wp, p.nxd + p.neq, -1.0, p.nineq, pa)
+    np.testing.assert_array_equal(M, W)
+    # and the whole system is a valid KKT system: inertia (nxd, 0, neq+nineq) for the dense block
+    ret_r, _, _, _ = ref.symdense_factor_solve(W)
+    ret, f = ko.mds_factorize_with_curv_check(M, Hxs)
+    assert ret == ret_r == p.neq + p.nineq
+    dx, dyc, dyd = ko.mds_solve_compressed(p, f, Hxs, p.rx, p.ryc, p.ryd)
+    # residual of the full (unreduced) XYcYd system
+    import scipy.sparse as sp
+    Jc = np.hstack([sp.csr_matrix((p.Jcs_vals, (p.iRow_c, p.jCol_c)), shape=(p.neq, p.nxs)).toarray(), p.Jcd])
+    Jd = np.hstack([sp.csr_matrix((p.Jds_vals, (p.iRow_d, p.jCol_d)), shape=(p.nineq, p.nxs)).toarray(), p.Jdd])
+    H = np.zeros((p.nxs + p.nxd, p.nxs + p.nxd))
+    H[:p.nxs, :p.nxs] = np.diag(p.Hs_diag)
+    H[p.nxs:, p.nxs:] = p.Hd
+    H += np.diag(Dx + p.delta_wx)
+    r1 = H @ dx + Jc.T @ dyc + Jd.T @ dyd - p.rx
+    r2 = Jc @ dx - p.delta_cc * dyc - p.ryc
+    r3 = Jd @ dx - (Dd_inv + p.delta_cd) * dyd - p.ryd
+    assert max(np.abs(r1).max(), np.abs(r2).max(), np.abs(r3).max()) <= 1e-9
