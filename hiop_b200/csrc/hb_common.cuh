@@ -120,12 +120,3 @@ __host__ __device__ inline long long hb_part_begin(long long total, int parts, i
 {
   return (total / parts) * p + (p < (int)(total % parts) ? p : (total % parts));
 }
-
-// internal cross-file API ------------------------------------------------------------------------------------
-// C(M x M, ldc) = A diag(d) A^T over this rank's columns; A is M x K row-major (lda), rows [0,M). Deterministic.
-// If `sym_full` both triangles are written, else only the upper triangle is valid.
-int hb_syrk_diag(hb_ctx* ctx, int M, long long K, const double* const* row_blocks, const int* row_block_rows, int n_blocks,
-                 long long lda, const double* d, double* C, int ldc);
-
-// dense factor / solve internals (hb_dense.cu)
-int hb_potrf_lower_rowmajor_upper(hb_ctx* ctx, int N, double* A, int lda, int* info_dev);
