@@ -17,6 +17,7 @@
 // slot; a second kernel sums the slots of each tile in a FIXED order and mirrors the result, so the output is
 // bit-reproducible run to run (no atomics).
 #include "hb_common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 k_syrk_diag(const double* const* __restrict__ rowptr, int M, long long K, const double* __restrict__ dvec, const Seg* __restrict__ segs,
             const int* __restrict__ cta_seg_begin, double* __restrict__ ws)
 {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   Stage* stages = reinterpret_cast<Stage*>(smem_raw);
   const double** srow_a = reinterpret_cast<const double**>(smem_raw + sizeof(Stage) * STAGES);
   const double** srow_b = srow_a + BM;
@@ -208,6 +209,169 @@ k_syrk_diag(const double* const* __restrict__ rowptr, int M, long long K, const 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Warp-specialised variant (the fast path): 8 MMA warps + 4 producer warps, mbarrier full/empty ring.
+// The producers issue 16-byte cp.async copies (zero-filling rows beyond M and the K tail through the src-size operand)
+// and signal the stage's mbarrier with cp.async.mbarrier.arrive.noinc; the MMA warps never execute a CTA-wide barrier
+// and never compute a global address, so they drift out of phase and keep the FP64 tensor pipe busy during refills.
+// (A first version staged rows with 256-byte cp.async.bulk copies from one producer warp: 288 bulk copies per stage
+// made the producer the bottleneck -- 61 ms vs 40 ms -- see profiles/README_r01.md.)
+// Needs 16-byte aligned rows (else k_syrk_diag<false> runs).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int WBK = 32;                 // doubles per K chunk
+constexpr int WSTAGES = 3;
+constexpr int WLDS = WBK + 4;           // 36 doubles = 288 B row stride (288 mod 128 = 32 -> conflict-free fragment reads)
+constexpr int WTILE_D = BM * WLDS;
+constexpr int WPROD = 128;              // producer threads (4 warps)
+constexpr int WTHREADS = 256 + WPROD;
+struct WStage
+{
+  double a[WTILE_D];
+  double b[WTILE_D];
+  double d[WBK];
+};
+constexpr size_t WSMEM_BYTES = sizeof(WStage) * WSTAGES + 2 * BM * sizeof(const double*) + 2 * WSTAGES * sizeof(unsigned long long);
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_on_cp_async(unsigned long long* bar)
+{
+  // arrives (without incrementing the pending count) once all prior cp.async of this thread have landed
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(WTHREADS, 1)
+k_syrk_ws(const double* const* __restrict__ rowptr, int M, long long K, const double* __restrict__ dvec, const Seg* __restrict__ segs,
+          const int* __restrict__ cta_seg_begin, double* __restrict__ ws)
+{
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  WStage* stages = reinterpret_cast<WStage*>(smem_raw);
+  const double** srow = reinterpret_cast<const double**>(smem_raw + sizeof(WStage) * WSTAGES); // [2*BM] row pointers (producers only)
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(srow + 2 * BM);
+  unsigned long long* empty = full + WSTAGES;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if(tid == 0) {
+#pragma unroll
+    for(int s = 0; s < WSTAGES; s++) {
+      mbar_init(&full[s], WPROD); // every producer thread arrives once its copies of the stage have landed
+      mbar_init(&empty[s], 8);    // one arrival per MMA warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int sb = cta_seg_begin[blockIdx.x], se = cta_seg_begin[blockIdx.x + 1];
+  int stage = 0;
+  unsigned phase = 0;
+
+  if(warp >= 8) {
+    // ================= producer warps =================
+    const int p = tid - 256;          // 0..127
+    const int kc = p & 15;            // 16-byte chunk within the 256-byte row segment
+    const int r0 = p >> 4;            // rows r0 + 8*j
+    for(int si = sb; si < se; si++) {
+      const Seg sg = segs[si];
+      const bool diag = sg.ti == sg.tj;
+      asm volatile("bar.sync 1, %0;\n" ::"n"(WPROD) : "memory"); // all producers done with the previous segment's row table
+      for(int r = p; r < 2 * BM; r += WPROD) {
+        const int grow = (r < BM ? sg.ti * BM + r : sg.tj * BM + (r - BM));
+        srow[r] = grow < M ? rowptr[grow] : nullptr;
+      }
+      asm volatile("bar.sync 1, %0;\n" ::"n"(WPROD) : "memory");
+      for(int it = 0; it < sg.k_count; it++) {
+        const long long k = ((long long)sg.k_begin + it) * WBK + kc * 2;
+        const long long rem = K - k;
+        const int nb = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
+        const long long koff = nb ? k : 0;
+        mbar_wait(&empty[stage], phase ^ 1);
+        WStage& st = stages[stage];
+#pragma unroll 4
+        for(int j = 0; j < 16; j++) {
+          const int row = r0 + 8 * j;
+          const double* pa = srow[row];
+          cp_async16(&st.a[row * WLDS + kc * 2], pa ? pa + koff : (const double*)rowptr, pa ? nb : 0);
+          if(!diag) {
+            const double* pb = srow[BM + row];
+            cp_async16(&st.b[row * WLDS + kc * 2], pb ? pb + koff : (const double*)rowptr, pb ? nb : 0);
+          }
+        }
+        if(p < 16 && dvec) cp_async16(&st.d[kc * 2], nb ? dvec + k : (const double*)rowptr, nb);
+        mbar_arrive_on_cp_async(&full[stage]);
+        if(++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+  } else {
+    // ================= 8 MMA warps =================
+    const int warp_m = warp & 1, warp_n = warp >> 1;
+    const int g = lane >> 2, t4 = lane & 3;
+    const bool unit_d = (dvec == nullptr);
+    for(int si = sb; si < se; si++) {
+      const Seg sg = segs[si];
+      const bool diag = sg.ti == sg.tj;
+      double acc[8][4][2];
+#pragma unroll
+      for(int i = 0; i < 8; i++)
+#pragma unroll
+        for(int j = 0; j < 4; j++) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for(int it = 0; it < sg.k_count; it++) {
+        mbar_wait(&full[stage], phase);
+        const WStage& st = stages[stage];
+        const double* sA = st.a + (warp_m * 64 + g) * WLDS + t4;
+        const double* sB = (diag ? st.a : st.b) + (warp_n * 32 + g) * WLDS + t4;
+#pragma unroll
+        for(int kk = 0; kk < WBK / 4; kk++) {
+          const double dv = unit_d ? 1.0 : st.d[kk * 4 + t4];
+          double af[8], bf[4];
+#pragma unroll
+          for(int i = 0; i < 8; i++) af[i] = sA[i * 8 * WLDS + kk * 4];
+#pragma unroll
+          for(int j = 0; j < 4; j++) bf[j] = sB[j * 8 * WLDS + kk * 4] * dv;
+#pragma unroll
+          for(int i = 0; i < 8; i++)
+#pragma unroll
+            for(int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+        __syncwarp();
+        if(lane == 0) mbar_arrive(&empty[stage]);
+        if(++stage == WSTAGES) { stage = 0; phase ^= 1; }
+      }
+      double* slot = ws + (size_t)sg.slot * (BM * BM);
+#pragma unroll
+      for(int i = 0; i < 8; i++) {
+        const int row = warp_m * 64 + i * 8 + g;
+#pragma unroll
+        for(int j = 0; j < 4; j++) {
+          const int col = warp_n * 32 + j * 8 + t4 * 2;
+          *reinterpret_cast<double2*>(slot + row * BM + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+      }
+    }
+  }
+}
+
 // Sums the partial slots of each tile in schedule order and writes C (both triangles).
 __global__ void __launch_bounds__(256)
 k_syrk_fixup(int M, const int2* __restrict__ tile_ij, const int* __restrict__ tile_slot_begin, const int* __restrict__ tile_slots,
@@ -233,6 +397,7 @@ struct Schedule
 {
   int M = -1;
   long long K = -1;
+  int bk = 0;      // K-chunk (columns per iteration) the schedule counts in
   int G = 0;       // SM count the schedule was built for
   int Gl = 0;      // CTAs to launch
   long long stamp = 0;
@@ -245,12 +410,12 @@ constexpr int SCHED_WAYS = 4;
 Schedule g_sched[16][SCHED_WAYS]; // per device, small LRU cache keyed by (M, K)
 long long g_sched_clock = 0;
 
-int build_schedule(hb_ctx* c, Schedule*& Sout, int M, long long K)
+int build_schedule(hb_ctx* c, Schedule*& Sout, int M, long long K, int bk)
 {
   Schedule* ways = g_sched[c->device];
   int victim = 0;
   for(int w = 0; w < SCHED_WAYS; w++) {
-    if(ways[w].M == M && ways[w].K == K && ways[w].G == c->num_sms) {
+    if(ways[w].M == M && ways[w].K == K && ways[w].bk == bk && ways[w].G == c->num_sms) {
       ways[w].stamp = ++g_sched_clock;
       Sout = &ways[w];
       return HB_OK;
@@ -264,7 +429,7 @@ int build_schedule(hb_ctx* c, Schedule*& Sout, int M, long long K)
   cudaFree(S.d_cta_seg_begin); cudaFree(S.d_tile_slot_begin); cudaFree(S.d_tile_slots); cudaFree(S.d_tile_ij); cudaFree(S.d_segs);
   const int T = (M + BM - 1) / BM;
   const int ntiles = T * (T + 1) / 2;
-  const long long kiters = (K + BK - 1) / BK;
+  const long long kiters = (K + bk - 1) / bk;
   const long long total = (long long)ntiles * kiters;
   int G = c->num_sms;
   if(total < G) G = (int)(total > 0 ? total : 1);
@@ -311,7 +476,7 @@ int build_schedule(hb_ctx* c, Schedule*& Sout, int M, long long K)
   HB_CUDA(cudaMemcpy(S.d_tile_slots, tsl.data(), sizeof(int) * tsl.size(), cudaMemcpyHostToDevice));
   HB_CUDA(cudaMemcpy(S.d_tile_ij, tij.data(), sizeof(int2) * ntiles, cudaMemcpyHostToDevice));
   HB_CUDA(cudaMemcpy(S.d_segs, segs.data(), sizeof(Seg) * segs.size(), cudaMemcpyHostToDevice));
-  S.M = M; S.K = K; S.G = c->num_sms; S.Gl = G; S.ntiles = ntiles; S.nslots = (int)cta_begin[G];
+  S.M = M; S.K = K; S.bk = bk; S.G = c->num_sms; S.Gl = G; S.ntiles = ntiles; S.nslots = (int)cta_begin[G];
   return HB_OK;
 }
 
@@ -330,18 +495,24 @@ int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev,
     return HB_OK;
   }
   HB_REQUIRE(c->device < 16, "device ordinal too large");
+  const bool d_aligned = (reinterpret_cast<uintptr_t>(d) & 15u) == 0;
+  const char* force_generic = getenv("HB_SYRK_GENERIC");
+  const bool use_ws = aligned16 && d_aligned && ((reinterpret_cast<uintptr_t>(rowptr_dev) & 15u) == 0) && !(force_generic && force_generic[0] == '1');
   Schedule* Sp = nullptr;
-  HB_CHECK(build_schedule(c, Sp, M, K));
+  HB_CHECK(build_schedule(c, Sp, M, K, use_ws ? WBK : BK));
   Schedule& S = *Sp;
   HB_CHECK(hb_ws_reserve(c, (size_t)S.nslots * BM * BM * sizeof(double)));
   if(!g_attr_set) {
     HB_CUDA(cudaFuncSetAttribute(k_syrk_diag<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     HB_CUDA(cudaFuncSetAttribute(k_syrk_diag<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    HB_CUDA(cudaFuncSetAttribute(k_syrk_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WSMEM_BYTES));
     g_attr_set = true;
   }
   const int G = S.Gl;
   if(c->timing) HB_CUDA(cudaEventRecord(c->ev_syrk0, c->stream));
-  if(aligned16 && ((reinterpret_cast<uintptr_t>(d) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(rowptr_dev) & 15u) == 0))
+  if(use_ws)
+    k_syrk_ws<<<G, WTHREADS, WSMEM_BYTES, c->stream>>>(rowptr_dev, M, K, d, S.d_segs, S.d_cta_seg_begin, (double*)c->ws);
+  else if(aligned16 && d_aligned && ((reinterpret_cast<uintptr_t>(rowptr_dev) & 15u) == 0))
     k_syrk_diag<true><<<G, THREADS, SMEM_BYTES, c->stream>>>(rowptr_dev, M, K, d, S.d_segs, S.d_cta_seg_begin, (double*)c->ws);
   else
     k_syrk_diag<false><<<G, THREADS, SMEM_BYTES, c->stream>>>(rowptr_dev, M, K, d, S.d_segs, S.d_cta_seg_begin, (double*)c->ws);
