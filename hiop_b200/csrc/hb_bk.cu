@@ -78,9 +78,17 @@ k_lasyf_panel(double* __restrict__ A, int lda, int N, double* __restrict__ W, in
     for(int c = tid; c < kl; c += PT) wrow[c] = WC(W, ldw, k, c);
     __syncthreads();
     for(int i = k + tid; i < N; i += PT) {
-      double v = LC(A, lda, i, k);
-      for(int c = 0; c < kl; c++) v -= LC(A, lda, i, k0 + c) * wrow[c];
-      WC(W, ldw, i, kl) = v;
+      double v = LC(A, lda, i, k), v1 = 0.0, v2 = 0.0, v3 = 0.0;
+      int c = 0;
+#pragma unroll 2
+      for(; c + 4 <= kl; c += 4) { // four independent accumulators: the loads of a batch are in flight together
+        v -= LC(A, lda, i, k0 + c) * wrow[c];
+        v1 -= LC(A, lda, i, k0 + c + 1) * wrow[c + 1];
+        v2 -= LC(A, lda, i, k0 + c + 2) * wrow[c + 2];
+        v3 -= LC(A, lda, i, k0 + c + 3) * wrow[c + 3];
+      }
+      for(; c < kl; c++) v -= LC(A, lda, i, k0 + c) * wrow[c];
+      WC(W, ldw, i, kl) = (v + v1) + (v2 + v3);
     }
     __syncthreads();
     int kstep = 1, kp = k;
@@ -106,9 +114,17 @@ k_lasyf_panel(double* __restrict__ A, int lda, int N, double* __restrict__ W, in
         for(int c = tid; c < kl; c += PT) wrow[c] = WC(W, ldw, imax, c);
         __syncthreads();
         for(int i = k + tid; i < N; i += PT) {
-          double v = i < imax ? LC(A, lda, imax, i) : LC(A, lda, i, imax);
-          for(int c = 0; c < kl; c++) v -= LC(A, lda, i, k0 + c) * wrow[c];
-          WC(W, ldw, i, kl + 1) = v;
+          double v = i < imax ? LC(A, lda, imax, i) : LC(A, lda, i, imax), v1 = 0.0, v2 = 0.0, v3 = 0.0;
+          int c = 0;
+#pragma unroll 2
+          for(; c + 4 <= kl; c += 4) {
+            v -= LC(A, lda, i, k0 + c) * wrow[c];
+            v1 -= LC(A, lda, i, k0 + c + 1) * wrow[c + 1];
+            v2 -= LC(A, lda, i, k0 + c + 2) * wrow[c + 2];
+            v3 -= LC(A, lda, i, k0 + c + 3) * wrow[c + 3];
+          }
+          for(; c < kl; c++) v -= LC(A, lda, i, k0 + c) * wrow[c];
+          WC(W, ldw, i, kl + 1) = (v + v1) + (v2 + v3);
         }
         __syncthreads();
         ArgMax a{-1.0, big};
@@ -210,9 +226,14 @@ k_bk_trailing(double* __restrict__ A, int lda, int N, const double* __restrict__
   const int kpad = ((kb + 3) / 4) * 4;
   for(int e = tid; e < kpad * TT; e += 128) {
     const int p = e / TT, c = e % TT;
-    sP[p][c] = (p < kb && i0 + c < N) ? LC(A, lda, i0 + c, k0 + p) : 0.0; // L21
-    sQ[p][c] = (p < kb && j0 + c < N) ? WC(W, ldw, j0 + c, p) : 0.0;      // W21
+    const bool vp = (p < kb) && (i0 + c < N), vq = (p < kb) && (j0 + c < N);
+    const unsigned sp = (unsigned)__cvta_generic_to_shared(&sP[p][c]), sq = (unsigned)__cvta_generic_to_shared(&sQ[p][c]);
+    const double* gp = vp ? &LC(A, lda, i0 + c, k0 + p) : A; // L21
+    const double* gq = vq ? &WC(W, ldw, j0 + c, p) : W;      // W21
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sp), "l"(gp), "r"(vp ? 8 : 0));
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sq), "l"(gq), "r"(vq ? 8 : 0));
   }
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
   const int wi = warp & 1, wj = warp >> 1;
@@ -233,6 +254,7 @@ k_bk_trailing(double* __restrict__ A, int lda, int N, const double* __restrict__
 #pragma unroll
       for(int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
   }
+  double cv[4][4][2];
 #pragma unroll
   for(int a = 0; a < 4; a++) {
     const int i = i0 + wi * 32 + a * 8 + g;
@@ -241,7 +263,18 @@ k_bk_trailing(double* __restrict__ A, int lda, int N, const double* __restrict__
 #pragma unroll
       for(int h = 0; h < 2; h++) {
         const int j = j0 + wj * 32 + b * 8 + t4 * 2 + h;
-        if(i < N && j < N && i >= j) LC(A, lda, i, j) -= acc[a][b][h];
+        cv[a][b][h] = (i < N && j < N && i >= j) ? LC(A, lda, i, j) : 0.0;
+      }
+  }
+#pragma unroll
+  for(int a = 0; a < 4; a++) {
+    const int i = i0 + wi * 32 + a * 8 + g;
+#pragma unroll
+    for(int b = 0; b < 4; b++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) {
+        const int j = j0 + wj * 32 + b * 8 + t4 * 2 + h;
+        if(i < N && j < N && i >= j) LC(A, lda, i, j) = cv[a][b][h] - acc[a][b][h];
       }
   }
 }

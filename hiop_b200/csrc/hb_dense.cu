@@ -38,32 +38,85 @@ k_panel(double* __restrict__ A, int lda, int N, int k0, int nb, double* __restri
   __shared__ double dinv[NB];
   const int tid = threadIdx.x;
   // load the lower part of the diagonal block; pad to identity beyond nb
-  for(int e = tid; e < NB * NB; e += PANEL_THREADS) {
-    const int j = e / NB, i = e % NB;
-    double v = (i == j) ? 1.0 : 0.0;
-    if(i < nb && j < nb && i >= j) v = LC(A, lda, k0 + i, k0 + j);
-    D[j][i] = v; // D[j][i] holds element (i,j)
+  {
+    double v[NB * NB / PANEL_THREADS];
+#pragma unroll
+    for(int q = 0; q < NB * NB / PANEL_THREADS; q++) { // all loads first (independent), then the stores
+      const int e = tid + q * PANEL_THREADS;
+      const int j = e / NB, i = e % NB;
+      v[q] = (i == j) ? 1.0 : 0.0;
+      if(i < nb && j < nb && i >= j) v[q] = LC(A, lda, k0 + i, k0 + j);
+    }
+#pragma unroll
+    for(int q = 0; q < NB * NB / PANEL_THREADS; q++) {
+      const int e = tid + q * PANEL_THREADS;
+      D[e / NB][e % NB] = v[q]; // D[j][i] holds element (i,j)
+    }
   }
   __syncthreads();
+  if(!LDL) {
+    // Blocked right-looking Cholesky of the 64x64 diagonal block in shared memory, 16-wide sub-panels, 3 barriers per
+    // sub-panel (12 in total instead of 2-3 per column):
+    //   (1) warp 0 factors the 16x16 diagonal sub-block in registers (lane r holds row r) with shuffles,
+    //   (2) one thread per row below solves its 16 entries against it,
+    //   (3) all threads apply the rank-16 update to the remaining lower triangle.
+    // D beyond nb is the identity, so a partial last panel needs no special casing.
+    const int lane = tid & 31, warp = tid >> 5;
+    for(int kb = 0; kb < NB; kb += 16) {
+      if(warp == 0) {
+        double a[16];
+#pragma unroll
+        for(int c = 0; c < 16; c++) a[c] = (lane < 16 && c <= lane) ? D[kb + c][kb + lane] : 0.0;
+#pragma unroll
+        for(int j = 0; j < 16; j++) {
+          const double d = __shfl_sync(0xffffffffu, a[j], j);
+          if(!(d > 0.0) && lane == 0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + kb + j + 1);
+          const double l = sqrt(d);
+          if(lane == j) a[j] = l;
+          else if(lane > j) a[j] = a[j] / l;
+#pragma unroll
+          for(int c = j + 1; c < 16; c++) {
+            const double lc = __shfl_sync(0xffffffffu, a[j], c);
+            if(lane >= c) a[c] -= a[j] * lc;
+          }
+        }
+#pragma unroll
+        for(int c = 0; c < 16; c++)
+          if(lane < 16 && c <= lane) D[kb + c][kb + lane] = a[c];
+      }
+      __syncthreads();
+      const int below = NB - kb - 16;
+      if(tid < below) {
+        const int r = kb + 16 + tid;
+        double x[16];
+#pragma unroll
+        for(int c = 0; c < 16; c++) x[c] = D[kb + c][r];
+#pragma unroll
+        for(int j = 0; j < 16; j++) {
+          x[j] /= D[kb + j][kb + j];
+          const double xj = x[j];
+#pragma unroll
+          for(int q = j + 1; q < 16; q++) x[q] -= xj * D[kb + j][kb + q];
+        }
+#pragma unroll
+        for(int c = 0; c < 16; c++) D[kb + c][r] = x[c];
+      }
+      __syncthreads();
+      for(int e = tid; e < below * below; e += PANEL_THREADS) {
+        const int c = kb + 16 + e / below, i = kb + 16 + e % below;
+        if(i >= c) {
+          double s = 0.0;
+#pragma unroll
+          for(int p = 0; p < 16; p++) s += D[kb + p][i] * D[kb + p][c];
+          D[c][i] -= s;
+        }
+      }
+      __syncthreads();
+    }
+  } else {
   for(int j = 0; j < nb; j++) {
     const double ajj = D[j][j];
-    if(!LDL) {
-      if(!(ajj > 0.0)) {
-        if(tid == 0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
-      }
-      const double r = 1.0 / sqrt(ajj);
-      __syncthreads();
-      if(tid == 0) D[j][j] = sqrt(ajj);
-      for(int i = j + 1 + tid; i < nb; i += PANEL_THREADS) D[j][i] *= r;
-      __syncthreads();
-      // trailing (i,c), j < c <= i < nb
-      const int rem = nb - j - 1;
-      for(int e = tid; e < rem * rem; e += PANEL_THREADS) {
-        const int c = j + 1 + e / rem, i = j + 1 + e % rem;
-        if(i >= c) D[c][i] -= D[j][i] * D[j][c];
-      }
-      __syncthreads();
-    } else {
+    {
       if(ajj == 0.0 || ajj != ajj) {
         if(tid == 0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + j + 1);
       }
@@ -81,6 +134,7 @@ k_panel(double* __restrict__ A, int lda, int N, int k0, int nb, double* __restri
       __syncthreads();
     }
   }
+  }
   if(blockIdx.x == 0) {
     for(int e = tid; e < nb * nb; e += PANEL_THREADS) {
       const int j = e / nb, i = e % nb;
@@ -93,13 +147,14 @@ k_panel(double* __restrict__ A, int lda, int N, int k0, int nb, double* __restri
     double x[NB];
 #pragma unroll
     for(int j = 0; j < NB; j++) x[j] = j < nb ? LC(A, lda, i, k0 + j) : 0.0;
+    // right-looking forward substitution: once x[j] is final, all later entries are updated independently (ILP 63..1
+    // instead of a dependent chain per entry)
 #pragma unroll
     for(int j = 0; j < NB; j++) {
-      double s = x[j];
+      if(!LDL) x[j] /= D[j][j];
+      const double xj = x[j];
 #pragma unroll
-      for(int p = 0; p < j; p++) s -= x[p] * D[p][j]; // element (j,p) of L11
-      if(!LDL) s /= D[j][j];
-      x[j] = s;
+      for(int q = j + 1; q < NB; q++) x[q] -= xj * D[j][q]; // element (q,j) of L11
     }
     if(LDL) {
 #pragma unroll
@@ -138,15 +193,20 @@ k_trailing(double* __restrict__ A, int lda, int N, int r0, const double* __restr
   (void)nt;
   const int i0 = r0 + ti * TT, j0 = r0 + tj * TT;
   const int tid = threadIdx.x;
-  for(int e = tid; e < kb * TT; e += 128) {
-    const int p = e / TT, c = e % TT;
-    sP[p][c] = (i0 + c < N) ? P[(size_t)p * ldp + i0 + c] : 0.0;
-    sQ[p][c] = (j0 + c < N) ? Q[(size_t)p * ldq + j0 + c] : 0.0;
-  }
-  for(int e = tid + kb * TT; e < ((kb + 3) / 4) * 4 * TT; e += 128) { // zero-pad K to a multiple of 4
-    const int p = e / TT, c = e % TT;
-    sP[p][c] = 0.0;
-    sQ[p][c] = 0.0;
+  {
+    // all 8-byte copies of the two operand tiles are issued back to back (one L2 latency for the whole tile instead of
+    // one per loop iteration); columns beyond N and the K padding are zero-filled through the src-size operand
+    const int kpad = ((kb + 3) / 4) * 4;
+    for(int e = tid; e < kpad * TT; e += 128) {
+      const int p = e / TT, c = e % TT;
+      const bool vp = (p < kb) && (i0 + c < N), vq = (p < kb) && (j0 + c < N);
+      const unsigned sp = (unsigned)__cvta_generic_to_shared(&sP[p][c]), sq = (unsigned)__cvta_generic_to_shared(&sQ[p][c]);
+      const double* gp = vp ? P + (size_t)p * ldp + i0 + c : P;
+      const double* gq = vq ? Q + (size_t)p * ldq + j0 + c : Q;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sp), "l"(gp), "r"(vp ? 8 : 0));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sq), "l"(gq), "r"(vq ? 8 : 0));
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
   }
   __syncthreads();
   const int lane = tid & 31, warp = tid >> 5;
@@ -169,17 +229,30 @@ k_trailing(double* __restrict__ A, int lda, int N, int r0, const double* __restr
 #pragma unroll
       for(int b = 0; b < 4; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
   }
+  // epilogue: all loads of the C tile first, then all stores (a load->sub->store chain per element would serialise on
+  // L2 latency because the compiler must assume the stores alias the following loads)
+  double cv[4][4][2];
 #pragma unroll
   for(int a = 0; a < 4; a++) {
     const int i = i0 + wi * 32 + a * 8 + g;
 #pragma unroll
-    for(int b = 0; b < 4; b++) {
+    for(int b = 0; b < 4; b++)
 #pragma unroll
       for(int h = 0; h < 2; h++) {
         const int j = j0 + wj * 32 + b * 8 + t4 * 2 + h;
-        if(i < N && j < N && i >= j) LC(A, lda, i, j) -= acc[a][b][h];
+        cv[a][b][h] = (i < N && j < N && i >= j) ? LC(A, lda, i, j) : 0.0;
       }
-    }
+  }
+#pragma unroll
+  for(int a = 0; a < 4; a++) {
+    const int i = i0 + wi * 32 + a * 8 + g;
+#pragma unroll
+    for(int b = 0; b < 4; b++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) {
+        const int j = j0 + wj * 32 + b * 8 + t4 * 2 + h;
+        if(i < N && j < N && i >= j) LC(A, lda, i, j) = cv[a][b][h] - acc[a][b][h];
+      }
   }
 }
 
@@ -189,24 +262,32 @@ k_trailing(double* __restrict__ A, int lda, int N, int r0, const double* __restr
 // ---------------------------------------------------------------------------------------------------------
 constexpr int SOLVE_THREADS = 1024;
 
-__device__ void dev_forward(const double* __restrict__ A, int lda, int N, double* x, bool unit_diag)
+// sd: 32 x 33 doubles of shared memory holding the current diagonal block (sd[c][r] = L(j0+r, j0+c)): one coalesced
+// load instead of 32 dependent L2 round trips inside the sequential part.
+__device__ void dev_forward(const double* __restrict__ A, int lda, int N, double* x, bool unit_diag, double (*sd)[33])
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for(int j0 = 0; j0 < N; j0 += 32) {
     const int nb = min(32, N - j0);
+    {
+      const int c = tid >> 5, r = tid & 31; // 1024 threads = one 32x32 block
+      if(c < nb && r < nb && r >= c) sd[c][r] = LC(A, lda, j0 + r, j0 + c);
+    }
+    __syncthreads();
     if(warp == 0) {
       double b = lane < nb ? x[j0 + lane] : 0.0;
       for(int c = 0; c < nb; c++) {
         double yc = __shfl_sync(0xffffffffu, b, c);
-        if(!unit_diag) yc /= LC(A, lda, j0 + c, j0 + c);
+        if(!unit_diag) yc /= sd[c][c];
         if(lane == c) b = yc;
-        if(lane > c && lane < nb) b -= LC(A, lda, j0 + lane, j0 + c) * yc;
+        if(lane > c && lane < nb) b -= sd[c][lane] * yc;
       }
       if(lane < nb) x[j0 + lane] = b;
     }
     __syncthreads();
     for(int i = j0 + nb + tid; i < N; i += SOLVE_THREADS) {
       double s = x[i];
+#pragma unroll 8
       for(int c = 0; c < nb; c++) s -= LC(A, lda, i, j0 + c) * x[j0 + c];
       x[i] = s;
     }
@@ -214,16 +295,22 @@ __device__ void dev_forward(const double* __restrict__ A, int lda, int N, double
   }
 }
 
-__device__ void dev_backward(const double* __restrict__ A, int lda, int N, double* x, bool unit_diag, double* sm32 /* 32 doubles */)
+__device__ void dev_backward(const double* __restrict__ A, int lda, int N, double* x, bool unit_diag, double* sm32 /* 32 doubles */,
+                             double (*sd)[33])
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nblk = (N + 31) / 32;
   for(int bi = nblk - 1; bi >= 0; bi--) {
     const int j0 = bi * 32;
     const int nb = min(32, N - j0);
+    {
+      const int c = tid >> 5, r = tid & 31;
+      if(c < nb && r < nb && r >= c) sd[c][r] = LC(A, lda, j0 + r, j0 + c);
+    }
     // each warp: dot of column (j0+warp) below the block with the already solved tail of x
     if(warp < nb) {
       double s = 0.0;
+#pragma unroll 8
       for(int i = j0 + nb + lane; i < N; i += 32) s += LC(A, lda, i, j0 + warp) * x[i];
       s = hb_warp_sum(s);
       if(lane == 0) sm32[warp] = s;
@@ -233,11 +320,11 @@ __device__ void dev_backward(const double* __restrict__ A, int lda, int N, doubl
       double b = lane < nb ? x[j0 + lane] - sm32[lane] : 0.0;
       for(int c = nb - 1; c >= 0; c--) {
         // x_c = (b_c - sum_{t>c} L(t,c) x_t) / L(c,c)
-        double part = (lane > c && lane < nb) ? LC(A, lda, j0 + lane, j0 + c) * b : 0.0;
+        double part = (lane > c && lane < nb) ? sd[c][lane] * b : 0.0;
         part = hb_warp_sum(part);
         if(lane == c) {
           b = b - part;
-          if(!unit_diag) b /= LC(A, lda, j0 + c, j0 + c);
+          if(!unit_diag) b /= sd[c][c];
         }
       }
       if(lane < nb) x[j0 + lane] = b;
@@ -254,14 +341,15 @@ k_spd_solve_refine(const double* __restrict__ F, int ldf, int N, const double* _
                    double* __restrict__ stats)
 {
   __shared__ double sm[32];
+  __shared__ double sd[32][33];
   __shared__ double s_nrm;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* r = work;       // residual / correction
   double* z = work + N;   // scaled rhs
   for(int i = tid; i < N; i += SOLVE_THREADS) z[i] = rhs[i] * s[i];
   __syncthreads();
-  dev_forward(F, ldf, N, z, false);
-  dev_backward(F, ldf, N, z, false, sm);
+  dev_forward(F, ldf, N, z, false, sd);
+  dev_backward(F, ldf, N, z, false, sm, sd);
   for(int i = tid; i < N; i += SOLVE_THREADS) x[i] = z[i] * s[i];
   __syncthreads();
   int nref = 0;
@@ -291,8 +379,8 @@ k_spd_solve_refine(const double* __restrict__ F, int ldf, int N, const double* _
     if(!(nrm >= tol) || nref >= max_refine) break; // also leaves on NaN
     for(int i = tid; i < N; i += SOLVE_THREADS) r[i] *= s[i];
     __syncthreads();
-    dev_forward(F, ldf, N, r, false);
-    dev_backward(F, ldf, N, r, false, sm);
+    dev_forward(F, ldf, N, r, false, sd);
+    dev_backward(F, ldf, N, r, false, sm, sd);
     for(int i = tid; i < N; i += SOLVE_THREADS) x[i] += r[i] * s[i];
     __syncthreads();
     nref++;
@@ -591,18 +679,27 @@ k_sytrs_cta(const double* __restrict__ A, int lda, int N, const int* __restrict_
 
 // Inertia sweep: BK factor -> LINPACK dsidi rule; no-pivot LDL^T / Cholesky -> signs of the diagonal.
 // out = {neg, null, pos}
-__global__ void k_inertia(const double* __restrict__ A, int lda, int N, const int* __restrict__ ipiv, int mode, int* __restrict__ out)
+__global__ void __launch_bounds__(1024)
+k_inertia(const double* __restrict__ A, int lda, int N, const int* __restrict__ ipiv, int mode, int* __restrict__ out, double* __restrict__ scratch)
 {
-  if(blockIdx.x != 0 || threadIdx.x != 0) return;
+  // scratch: 2N doubles (diagonal, sub-diagonal), gathered by all threads (strided loads in parallel)
+  double* dg = scratch;
+  double* sub = scratch + N;
+  for(int k = threadIdx.x; k < N; k += blockDim.x) {
+    dg[k] = LC(A, lda, k, k);
+    sub[k] = (k + 1 < N) ? LC(A, lda, k + 1, k) : 0.0;
+  }
+  __syncthreads();
+  if(threadIdx.x != 0) return;
   int neg = 0, nul = 0, pos = 0;
   double t = 0.0;
   for(int k = 0; k < N; k++) {
-    double d = LC(A, lda, k, k);
+    double d = dg[k];
     if(mode == HB_FACT_BUNCH_KAUFMAN && ipiv[k] <= 0) {
       if(t == 0.0) {
         if(k + 1 < N) {
-          t = fabs(LC(A, lda, k + 1, k));
-          d = (d / t) * LC(A, lda, k + 1, k + 1) - t;
+          t = fabs(sub[k]);
+          d = (d / t) * dg[k + 1] - t;
         }
       } else {
         d = t;
@@ -621,17 +718,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS)
 k_ldl_solve(const double* __restrict__ F, int ldf, int N, double* __restrict__ x)
 {
   __shared__ double sm[32];
-  dev_forward(F, ldf, N, x, true);
+  __shared__ double sd[32][33];
+  dev_forward(F, ldf, N, x, true, sd);
   for(int i = threadIdx.x; i < N; i += SOLVE_THREADS) x[i] /= LC(F, ldf, i, i);
   __syncthreads();
-  dev_backward(F, ldf, N, x, true, sm);
+  dev_backward(F, ldf, N, x, true, sm, sd);
 }
 __global__ void __launch_bounds__(SOLVE_THREADS)
 k_chol_solve(const double* __restrict__ F, int ldf, int N, double* __restrict__ x)
 {
   __shared__ double sm[32];
-  dev_forward(F, ldf, N, x, false);
-  dev_backward(F, ldf, N, x, false, sm);
+  __shared__ double sd[32][33];
+  dev_forward(F, ldf, N, x, false, sd);
+  dev_backward(F, ldf, N, x, false, sm, sd);
 }
 
 } // namespace
@@ -694,7 +793,8 @@ int hb_dense_sytrs(hb_ctx* c, int N, const double* A, int lda, const int* ipiv_d
 
 int hb_dense_inertia(hb_ctx* c, int N, const double* A, int lda, const int* ipiv_dev, int mode, int* out3_dev)
 {
-  k_inertia<<<1, 32, 0, c->stream>>>(A, lda, N, ipiv_dev, mode, out3_dev);
+  HB_CHECK(hb_ws_reserve(c, sizeof(double) * 2 * (size_t)(N > 0 ? N : 1) + 256));
+  k_inertia<<<1, 1024, 0, c->stream>>>(A, lda, N, ipiv_dev, mode, out3_dev, reinterpret_cast<double*>(reinterpret_cast<char*>(c->ws) + 256));
   HB_LAUNCHED();
   return HB_OK;
 }
