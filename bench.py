@@ -257,6 +257,8 @@ def run_engine(args):
     k.set_patterns(T["ixl"], T["ixu"], T["idl"], T["idu"])
     k.set_jacobian(T["J"][:m_eq], T["J"][m_eq:])
     k.set_secant(1.0, T["St"] if l else None, T["Yt"] if l else None, T["L"], T["D"])
+    if args.condense != "dmma":
+        k.set_condense_mode(int(args.condense[2]))
     ctx.enable_timing(True)
     rx_work = ctx.zeros(n_local)
     dx, dyc, dyd = ctx.zeros(n_local), ctx.zeros(m_eq), ctx.zeros(m_ineq)
@@ -376,6 +378,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_FULL)
     ap.add_argument("--m", type=int, default=M_FULL)
     ap.add_argument("--l", type=int, default=L_MEM)
+    ap.add_argument("--condense", default="dmma", choices=["dmma", "oz6", "oz7", "oz8"],
+                    help="GEMM part of the condensation: exact FP64 DMMA, or INT8-slice tcgen05 with 6/7/8 slices")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="columns of the workload the CPU baseline leg runs")

@@ -3,8 +3,10 @@
 // hiopKKTLinSysCompressedXYcYd::computeDirections hiopKKTLinSys.cpp:585-691, compute_directions_for_full_space :218-309.
 #include "hb_common.cuh"
 #include "hb_dense.cuh"
+#include <cstdlib>
 
 int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool aligned16, const double* d, double* C, int ldc);
+int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool rows_aligned16, const double* d, double* C, int ldc, int S);
 
 namespace {
 
@@ -339,6 +341,7 @@ struct hb_lowrank
   double *mi1 = nullptr, *mi2 = nullptr, *mi3 = nullptr; // m_ineq scratch
   int md_grid = 0;
   bool have_update = false, cond_valid = false, mdir_valid = false;
+  int condense_mode = 0; // 0 = FP64 DMMA, 6/7/8 = INT8-slice tcgen05
   // host staging (hb_lowrank_kkt_system_host)
   double* hbuf[16] = {nullptr};
   double* hJ = nullptr;
@@ -452,7 +455,8 @@ int do_condense(hb_lowrank* k)
   HB_CHECK(refresh_rowptr(k));
   HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
   if(Ma > 0) {
-    HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
+    if(k->condense_mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
+    else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, k->condense_mode));
     HB_CHECK(hb_allreduce_sum(c, k->Caug, (long long)Ma * Ma));
   }
   if(l > 0) {
@@ -492,6 +496,9 @@ extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_i
   HB_CUDA(cudaSetDevice(c->device));
   hb_lowrank* k = new hb_lowrank;
   k->ctx = c; k->n = n_local; k->meq = m_eq; k->mineq = m_ineq; k->m = m_eq + m_ineq; k->lmax = l_max;
+  if(const char* e = getenv("HB_CONDENSE")) { // "oz6" | "oz7" | "oz8" | "dmma"
+    if(e[0] == 'o' && e[1] == 'z' && e[2] >= '6' && e[2] <= '8') k->condense_mode = e[2] - '0';
+  }
   const int m = k->m, Mamax = m + 2 * l_max, l2 = 2 * l_max;
   HB_CHECK(dmalloc(&k->Dx, n_local)); HB_CHECK(dmalloc(&k->DhInv, n_local));
   HB_CHECK(dmalloc(&k->Dd, m_ineq)); HB_CHECK(dmalloc(&k->Dd_inv, m_ineq));
@@ -608,6 +615,14 @@ extern "C" int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* 
     HB_LAUNCHED();
   }
   k->have_update = true;
+  k->cond_valid = false;
+  return HB_OK;
+}
+
+extern "C" int hb_lowrank_set_condense_mode(hb_lowrank* k, int mode)
+{
+  HB_REQUIRE(k && (mode == 0 || mode == 6 || mode == 7 || mode == 8), "hb_lowrank_set_condense_mode: mode must be 0, 6, 7 or 8");
+  k->condense_mode = mode;
   k->cond_valid = false;
   return HB_OK;
 }

@@ -239,6 +239,10 @@ class KKTLinSysLowRank:
         check(self.ctx.L.hb_lowrank_update(self.h, *[_ptr(t) for t in (zl, sxl, zu, sxu, vl, sdl, vu, sdu)]), "hb_lowrank_update")
         return True
 
+    def set_condense_mode(self, mode: int):
+        """0 = exact FP64 on the DMMA pipe (default); 6/7/8 = INT8-slice emulation on tcgen05 with that many slices."""
+        check(self.ctx.L.hb_lowrank_set_condense_mode(self.h, int(mode)), "hb_lowrank_set_condense_mode")
+
     def condense(self):
         check(self.ctx.L.hb_lowrank_condense(self.h), "hb_lowrank_condense")
 
