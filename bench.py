@@ -137,22 +137,80 @@ def run_reference(args):
 # GPU arm
 # -----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed region: NVML from a thread every 5 ms (an nvidia-smi
+    subprocess needs >100 ms per sample, longer than a short timed region), nvidia-smi -lms as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
         self.idx = device_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.f = None
+        self.thread = None
+        self.samples = []
+        self.smax = None
+        self.reason_bits = 0
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES remaps cuda indices; resolve through the PCI bus id of the torch device
+            import torch
+            bus = getattr(torch.cuda.get_device_properties(device_index), "pci_bus_id", None)
+            self.h = None
+            if bus is not None:
+                for i in range(pynvml.nvmlDeviceGetCount()):
+                    h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                    if int(pynvml.nvmlDeviceGetPciInfo(h).bus) == int(bus):
+                        self.h, self.idx = h, i
+            if self.h is None:
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop(self):
+        nv = self.nvml
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                try:
+                    self.reason_bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:
+                    pass
+            time.sleep(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            import threading
+            self._stop = False
+            self.thread = threading.Thread(target=self._loop, daemon=True)
+            self.thread.start()
+            return
         try:
+            self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
             self.p = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            nv = self.nvml
+            names = (("hw_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+                     ("hw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+                     ("sw_thermal_slowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+                     ("sw_power_cap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)))
+            reasons = sorted(n for n, bit in names if self.reason_bits & bit)
+            sm_sorted = sorted(self.samples)
+            load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
+            return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": self.smax, "reasons": reasons,
+                    "samples": len(self.samples), "source": "nvml"}
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -177,7 +235,8 @@ class ClockSampler:
         # under load = upper half of the samples
         sm_sorted = sorted(sm)
         load = sm_sorted[len(sm_sorted) // 2:] if sm_sorted else []
-        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def make_device_problem(ctx, torch, n_local, n_total, m, l, rank, world, dist):
@@ -257,7 +316,9 @@ def run_engine(args):
     k.set_patterns(T["ixl"], T["ixu"], T["idl"], T["idu"])
     k.set_jacobian(T["J"][:m_eq], T["J"][m_eq:])
     k.set_secant(1.0, T["St"] if l else None, T["Yt"] if l else None, T["L"], T["D"])
-    if args.condense != "dmma":
+    if args.condense == "dmma":
+        k.set_condense_mode(0)
+    elif args.condense != "auto":
         k.set_condense_mode(int(args.condense[2]))
     ctx.enable_timing(True)
     rx_work = ctx.zeros(n_local)
@@ -343,14 +404,34 @@ def run_engine(args):
     Ma = m + 2 * l
     syrk = statistics.mean(syrk_ms)
     fl = flops_syrk(n_local, Ma)
-    achieved = fl / (syrk * 1e-3) / 1e12
-    roofline = {"kernel": "k_syrk_diag (FP64 DMMA.8x8x4 condensation [J;S;Y] DhInv [J;S;Y]^T)", "bound": "tensor", "achieved": achieved,
-                "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
-                "kernel_ms": syrk, "kernel_share_of_step": syrk / ms_step,
-                "flops_per_launch": fl,
-                "peak_source": "FP64 tensor (DMMA) peak measured on this pool's B200 by tools/microbench_fp64.cu = 64 FMA/clk/SM x 148 SMs x "
-                               "1965 MHz; MEASURED_PEAKS.json holds only HBM and bf16 numbers (tcgen05 has no f64 kind)",
-                "hbm_algorithmic_GBs_whole_step": algorithmic_bytes(n_local, m, l) / (ms_step * 1e-3) / 1e9}
+    mode = k.condense_mode_used()
+    if mode == 0:
+        achieved = fl / (syrk * 1e-3) / 1e12
+        roofline = {"kernel": "k_syrk_ws (FP64 DMMA.8x8x4 condensation [J;S;Y] DhInv [J;S;Y]^T)", "bound": "tensor", "achieved": achieved,
+                    "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                    "kernel_ms": syrk, "kernel_share_of_step": syrk / ms_step, "flops_per_launch": fl,
+                    "peak_source": "FP64 tensor (DMMA) peak measured on this pool's B200 by tools/microbench_fp64.cu = 64 FMA/clk/SM x 148 SMs x "
+                                   "1965 MHz; MEASURED_PEAKS.json holds only HBM and bf16 numbers (tcgen05 has no f64 kind)"}
+    else:
+        # INT8-slice emulation on tcgen05. Algorithmic integer work = the S(S+1)/2 slice products kept by the truncation
+        # rule over the Ma(Ma+1)/2 output entries of the symmetric result, 2 ops per MAC (tile padding and the below-diagonal
+        # halves of the diagonal tiles are executed but not counted).
+        ops = 2.0 * (mode * (mode + 1) // 2) * (Ma * (Ma + 1) / 2) * n_local
+        Mpad = (Ma + 127) // 128 * 128
+        ntiles = sum(1 for bi in range(Mpad // 128) for bj in range(2 * bi, Mpad // 64) if bj * 64 < Ma)
+        ops_executed = 2.0 * (mode * (mode + 1) // 2) * ntiles * 128 * 64 * ((n_local + 127) // 128 * 128)
+        peak = 4500.0
+        achieved = ops / (syrk * 1e-3) / 1e12
+        roofline = {"kernel": f"k_oz_gemm<{mode}> (tcgen05.mma.kind::i8, {mode} int8 slices, TMA SWIZZLE_128B, TMEM accumulators)", "bound": "tensor",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None, "kernel_ms": syrk,
+                    "kernel_share_of_step": syrk / ms_step, "flops_per_launch": ops, "executed_ops_per_launch": ops_executed,
+                    "executed_rate": ops_executed / (syrk * 1e-3) / 1e12,
+                    "peak_source": "nominal dense int8 tcgen05 rate of B200, 4.5 POP/s (fallback: MEASURED_PEAKS.json has no int8 figure; "
+                                   "2 x its bf16_tflops = 3403 is below what this kernel executes, so it is not usable as a ceiling)",
+                    "note": "achieved/peak count int8 operations (2 per MAC); the FP64 work the kernel stands in for is fp64_equivalent_flops",
+                    "fp64_equivalent_flops": fl, "fp64_equivalent_tflops_gemm_only": fl / (syrk * 1e-3) / 1e12}
+    roofline["hbm_algorithmic_GBs_whole_step"] = algorithmic_bytes(n_local, m, l) / (ms_step * 1e-3) / 1e9
+    roofline["condense_mode"] = "fp64_dmma" if mode == 0 else f"int8_slices_{mode}"
     line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"synthetic NlpDenseConsEx2 generalisation n={n} m={m} (m_eq={m_eq}, m_ineq={m_ineq}) l={l}: "
@@ -378,8 +459,8 @@ def main():
     ap.add_argument("--n", type=int, default=N_FULL)
     ap.add_argument("--m", type=int, default=M_FULL)
     ap.add_argument("--l", type=int, default=L_MEM)
-    ap.add_argument("--condense", default="dmma", choices=["dmma", "oz6", "oz7", "oz8"],
-                    help="GEMM part of the condensation: exact FP64 DMMA, or INT8-slice tcgen05 with 6/7/8 slices")
+    ap.add_argument("--condense", default="auto", choices=["auto", "dmma", "oz6", "oz7", "oz8"],
+                    help="GEMM part of the condensation: auto (library default), exact FP64 DMMA, or INT8-slice tcgen05 with 6/7/8 slices")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=20000, help="columns of the workload the CPU baseline leg runs")

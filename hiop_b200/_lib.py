@@ -118,6 +118,7 @@ def lib() -> ctypes.CDLL:
     f("hb_lowrank_update", c_i, c_vp, *([c_dp] * 8))
     f("hb_lowrank_condense", c_i, c_vp)
     f("hb_lowrank_set_condense_mode", c_i, c_vp, c_i)
+    f("hb_lowrank_get_condense_mode", c_i, c_vp)
     f("hb_lowrank_solve_compressed", c_i, c_vp, *([c_dp] * 6))
     f("hb_lowrank_compute_directions", c_i, c_vp, P(c_vp), P(c_vp))
     f("hb_lowrank_hess_solve", c_i, c_vp, c_dp, c_dp)

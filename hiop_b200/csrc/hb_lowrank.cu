@@ -341,7 +341,8 @@ struct hb_lowrank
   double *mi1 = nullptr, *mi2 = nullptr, *mi3 = nullptr; // m_ineq scratch
   int md_grid = 0;
   bool have_update = false, cond_valid = false, mdir_valid = false;
-  int condense_mode = 0; // 0 = FP64 DMMA, 6/7/8 = INT8-slice tcgen05
+  int condense_mode = -1; // -1 = auto, 0 = FP64 DMMA, 6/7/8 = INT8-slice tcgen05
+  int condense_used = 0;
   // host staging (hb_lowrank_kkt_system_host)
   double* hbuf[16] = {nullptr};
   double* hJ = nullptr;
@@ -455,8 +456,11 @@ int do_condense(hb_lowrank* k)
   HB_CHECK(refresh_rowptr(k));
   HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
   if(Ma > 0) {
-    if(k->condense_mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
-    else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, k->condense_mode));
+    int mode = k->condense_mode;
+    if(mode < 0) mode = (k->n >= 32768 && Ma >= 64) ? 8 : 0; // small systems: slicing + TMA setup do not pay off
+    k->condense_used = mode;
+    if(mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
+    else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, mode));
     HB_CHECK(hb_allreduce_sum(c, k->Caug, (long long)Ma * Ma));
   }
   if(l > 0) {
@@ -498,6 +502,7 @@ extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_i
   k->ctx = c; k->n = n_local; k->meq = m_eq; k->mineq = m_ineq; k->m = m_eq + m_ineq; k->lmax = l_max;
   if(const char* e = getenv("HB_CONDENSE")) { // "oz6" | "oz7" | "oz8" | "dmma"
     if(e[0] == 'o' && e[1] == 'z' && e[2] >= '6' && e[2] <= '8') k->condense_mode = e[2] - '0';
+    else if(e[0] == 'd') k->condense_mode = 0;
   }
   const int m = k->m, Mamax = m + 2 * l_max, l2 = 2 * l_max;
   HB_CHECK(dmalloc(&k->Dx, n_local)); HB_CHECK(dmalloc(&k->DhInv, n_local));
@@ -621,11 +626,13 @@ extern "C" int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* 
 
 extern "C" int hb_lowrank_set_condense_mode(hb_lowrank* k, int mode)
 {
-  HB_REQUIRE(k && (mode == 0 || mode == 6 || mode == 7 || mode == 8), "hb_lowrank_set_condense_mode: mode must be 0, 6, 7 or 8");
+  HB_REQUIRE(k && (mode == -1 || mode == 0 || mode == 6 || mode == 7 || mode == 8), "hb_lowrank_set_condense_mode: mode must be -1, 0, 6, 7 or 8");
   k->condense_mode = mode;
   k->cond_valid = false;
   return HB_OK;
 }
+
+extern "C" int hb_lowrank_get_condense_mode(hb_lowrank* k) { return k ? k->condense_used : 0; }
 
 extern "C" int hb_lowrank_condense(hb_lowrank* k)
 {

@@ -240,8 +240,11 @@ class KKTLinSysLowRank:
         return True
 
     def set_condense_mode(self, mode: int):
-        """0 = exact FP64 on the DMMA pipe (default); 6/7/8 = INT8-slice emulation on tcgen05 with that many slices."""
+        """-1 = auto (default); 0 = exact FP64 on the DMMA pipe; 6/7/8 = INT8-slice emulation on tcgen05 with that many slices."""
         check(self.ctx.L.hb_lowrank_set_condense_mode(self.h, int(mode)), "hb_lowrank_set_condense_mode")
+
+    def condense_mode_used(self) -> int:
+        return int(self.ctx.L.hb_lowrank_get_condense_mode(self.h))
 
     def condense(self):
         check(self.ctx.L.hb_lowrank_condense(self.h), "hb_lowrank_condense")

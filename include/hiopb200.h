@@ -181,11 +181,14 @@ int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* sxl, const 
  * Returns HB_ERR_NUMERIC if N is not numerically SPD. */
 int hb_lowrank_condense(hb_lowrank* k);
 /* How the GEMM-shaped part of the condensation is computed:
- *   HB_CONDENSE_FP64_DMMA (0, default): exact FP64 on the DMMA pipe (mma.sync.m8n8k4.f64);
+ *   HB_CONDENSE_FP64_DMMA (0): exact FP64 on the DMMA pipe (mma.sync.m8n8k4.f64);
  *   6, 7, 8: INT8-slice (Ozaki) emulation on the tcgen05 tensor cores with that many 7-bit slices -- exact integer
  *   products/accumulation in TMEM, truncation of the operands 2^-41 / 2^-48 / 2^-55 relative to each row's largest entry. */
+#define HB_CONDENSE_AUTO (-1)      /* default: 8 slices on tcgen05 when n_local >= 32768 and m+2l >= 64, FP64 DMMA otherwise */
 #define HB_CONDENSE_FP64_DMMA 0
 int hb_lowrank_set_condense_mode(hb_lowrank* k, int mode);
+/* the mode the last hb_lowrank_condense actually used (0, 6, 7 or 8) */
+int hb_lowrank_get_condense_mode(hb_lowrank* k);
 /* solveCompressed(rx,ryc,ryd -> dx,dyc,dyd) (hiopKKTLinSys.cpp:1110-1190) incl. the residual-driven refinement of
  * solveWithRefin (:1192-1350: ||rhs - N x||_inf < 1e-8, <= 3 corrections). Condenses first if the cache is stale.
  * Like the reference, rx is used as scratch and overwritten (:1178). */
