@@ -363,6 +363,21 @@ def run_engine(args):
         ms_step = ms_total / args.steps
         nref, resid = k.last_solve_stats()
 
+        # ---- parity gate of SURVEY 8(d), outside the timed region: relative residual of the 3-block compressed KKT system of the
+        # last step, evaluated with FP64 operators that do not depend on the condensed matrix or its factor (compact-form B*x +
+        # Dx*x, plain J gemvs; n-sharded with the same all-reduces) ----
+        r1 = T["rx"].clone()
+        r1.mul_(-1.0)
+        k.hess_times_vec(1.0, r1, 1.0, dx, True)                              # (B + Dx) dx - rx
+        ctx.mat_trans_times_vec(T["J"][:m_eq], 1.0, r1, 1.0, dyc)
+        ctx.mat_trans_times_vec(T["J"][m_eq:], 1.0, r1, 1.0, dyd)
+        r2, r3 = T["ryc"].clone(), T["ryd"].clone()
+        ctx.mat_times_vec(T["J"][:m_eq], -1.0, r2, 1.0, dx)                   # Jc dx - ryc
+        ctx.mat_times_vec(T["J"][m_eq:], -1.0, r3, 1.0, dx)                   # Jd dx - Dd^-1 dyd - ryd
+        ctx.vec_axzpy(r3, -1.0, ctx.to_device(k.Dd_inv()), dyd)
+        scale = max(ctx.vec_infnorm(T["rx"]), float(T["ryc"].abs().max()), float(T["ryd"].abs().max()))
+        kkt_resid_rel = max(ctx.vec_infnorm(r1), float(r2.abs().max()), float(r3.abs().max())) / scale
+
         # ---- end to end through the host-buffer entry point (public API a HiOp adapter calls when mem_space is host) ----
         e2e = None
         if world == 1 and not args.no_e2e:
@@ -438,7 +453,7 @@ def run_engine(args):
                                    "quasi-Newton condensed KKT, update+condense+Cholesky+solve every step",
                        "parallelism": f"column-sharded x{world}" if world > 1 else "single GPU",
                        "l2": f"J is {8e-9 * m * n_local:.1f} GB per GPU, far larger than the 126 MB L2; no flush needed",
-                       "refinement_steps_last": nref, "residual_inf_last": resid},
+                       "refinement_steps_last": nref, "residual_inf_last": resid, "kkt_residual_rel_fp64_operators": kkt_resid_rel},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline}
     if e2e is not None:
         line["e2e"] = e2e
