@@ -127,41 +127,80 @@ __global__ void k_sqrt(long long n, const double* __restrict__ d, double* __rest
   for(long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) sd[i] = sqrt(d[i]);
 }
 
-// Q[p][row][k] (int8, row pitch Kpad bytes, slice pitch Mpad*Kpad). One thread = 4 consecutive k of one row: a warp reads
-// 1 KB of the FP64 row with 16-byte loads and writes 128 contiguous bytes per slice.
+// Q[p][row][k] (int8, row pitch Kpad bytes, slice pitch Mpad*Kpad). One thread = 8 consecutive k of one row: a warp reads
+// 2 KB of the FP64 row with 16-byte loads and writes 256 contiguous bytes per slice.
+//
+// Digits without the conversion pipe: with b = a*sd / 2^e (|b| < 1), hi = rint(b * 2^27) carries the first four slices
+// (6+7+7+7 bits) and lo = rint((b*2^27 - hi) * 2^(7(S-4))) the remaining S-4. Both roundings use the 1.5*2^52 magic-number
+// add (two DADDs at full FP64 rate; the integer is the low word of the sum -- no F2I/FRND, which issue at 1/4 rate and made
+// the first version of this kernel conversion-bound at 3.9 ms for 8 GB). Each 32-bit integer is then cut into balanced
+// base-128 digits d in [-64, 63] from the least significant end; the leading digit of either word is bounded by 64.
+// sum_p q_p 2^-(6+7p) = b rounded to the last slice's grid, exactly.
+template <int ND>
+__device__ __forceinline__ void oz_digits(int v, int (&d)[ND])
+{
+#pragma unroll
+  for(int j = ND - 1; j > 0; j--) {
+    d[j] = ((v + 64) & 127) - 64;
+    v = (v - d[j]) >> 7;
+  }
+  d[0] = v;
+}
 template <int S>
 __global__ void __launch_bounds__(256)
 k_oz_slice(const double* const* __restrict__ rowptr, int M, int Mpad, long long K, long long Kpad, const double* __restrict__ sd,
            const int* __restrict__ e, int8_t* __restrict__ Q, int vec_ok)
 {
+  static_assert(S >= 5 && S <= 8, "slices");
+  constexpr int NLO = S - 4;
   const int row = blockIdx.y;
-  const long long k0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 4;
+  const long long k0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
   if(k0 >= Kpad) return;
-  double x[4] = {0.0, 0.0, 0.0, 0.0};
+  double x[8];
+#pragma unroll
+  for(int j = 0; j < 8; j++) x[j] = 0.0;
   if(row < M) {
     const double* a = rowptr[row];
-    const double sc = ldexp(1.0, -e[row]) * 64.0; // first slice keeps 6 bits: |x*64| <= 64
-    if(vec_ok && k0 + 3 < K) {
-      const double2 a0 = *reinterpret_cast<const double2*>(a + k0), a1 = *reinterpret_cast<const double2*>(a + k0 + 2);
-      double2 s0 = make_double2(1.0, 1.0), s1 = s0;
-      if(sd) { s0 = *reinterpret_cast<const double2*>(sd + k0); s1 = *reinterpret_cast<const double2*>(sd + k0 + 2); }
-      x[0] = a0.x * s0.x * sc; x[1] = a0.y * s0.y * sc; x[2] = a1.x * s1.x * sc; x[3] = a1.y * s1.y * sc;
+    const double sc = ldexp(1.0, 27 - e[row]);
+    if(vec_ok && k0 + 7 < K) {
+#pragma unroll
+      for(int j = 0; j < 8; j += 2) {
+        const double2 av = *reinterpret_cast<const double2*>(a + k0 + j);
+        double2 sv = make_double2(1.0, 1.0);
+        if(sd) sv = *reinterpret_cast<const double2*>(sd + k0 + j);
+        x[j] = __dmul_rn(__dmul_rn(av.x, sv.x), sc);
+        x[j + 1] = __dmul_rn(__dmul_rn(av.y, sv.y), sc);
+      }
     } else {
 #pragma unroll
-      for(int j = 0; j < 4; j++)
-        if(k0 + j < K) x[j] = a[k0 + j] * (sd ? sd[k0 + j] : 1.0) * sc;
+      for(int j = 0; j < 8; j++)
+        if(k0 + j < K) x[j] = __dmul_rn(__dmul_rn(a[k0 + j], sd ? sd[k0 + j] : 1.0), sc);
     }
   }
+  const double MAGIC = 6755399441055744.0; // 1.5 * 2^52
+  unsigned w[S][2];
 #pragma unroll
-  for(int p = 0; p < S; p++) {
-    char4 q;
-    double r;
-    r = rint(x[0]); q.x = (signed char)(int)r; x[0] = (x[0] - r) * 128.0; // exact: |x - r| <= 0.5, power-of-two scaling
-    r = rint(x[1]); q.y = (signed char)(int)r; x[1] = (x[1] - r) * 128.0;
-    r = rint(x[2]); q.z = (signed char)(int)r; x[2] = (x[2] - r) * 128.0;
-    r = rint(x[3]); q.w = (signed char)(int)r; x[3] = (x[3] - r) * 128.0;
-    *reinterpret_cast<char4*>(Q + ((size_t)p * Mpad + row) * Kpad + k0) = q;
+  for(int h = 0; h < 2; h++) {
+    int dh[4][4], dl[4][NLO];
+#pragma unroll
+    for(int j = 0; j < 4; j++) {
+      const double xs = x[4 * h + j];
+      const double t = __dadd_rn(xs, MAGIC);
+      const int hi = __double2loint(t);
+      const double rem = __dsub_rn(xs, __dsub_rn(t, MAGIC));                       // exact, |rem| <= 0.5
+      const int lo = __double2loint(__fma_rn(rem, (double)(1 << (7 * NLO)), MAGIC));
+      oz_digits<4>(hi, dh[j]);
+      oz_digits<NLO>(lo, dl[j]);
+    }
+#pragma unroll
+    for(int p = 0; p < 4; p++)
+      w[p][h] = __byte_perm(__byte_perm(dh[0][p], dh[1][p], 0x0040), __byte_perm(dh[2][p], dh[3][p], 0x0040), 0x5410);
+#pragma unroll
+    for(int p = 0; p < NLO; p++)
+      w[4 + p][h] = __byte_perm(__byte_perm(dl[0][p], dl[1][p], 0x0040), __byte_perm(dl[2][p], dl[3][p], 0x0040), 0x5410);
   }
+#pragma unroll
+  for(int p = 0; p < S; p++) *reinterpret_cast<uint2*>(Q + ((size_t)p * Mpad + row) * Kpad + k0) = make_uint2(w[p][0], w[p][1]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -492,7 +531,7 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
     HB_LAUNCHED();
     k_oz_exponents<<<(Mpad + 127) / 128, 128, 0, c->stream>>>(M, st.mx, st.e);
     HB_LAUNCHED();
-    const unsigned sx = (unsigned)((Kpad / 4 + 255) / 256);
+    const unsigned sx = (unsigned)((Kpad / 8 + 255) / 256);
     const int vec_ok = rows_aligned16 ? 1 : 0;
     if(S == 6) k_oz_slice<6><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
     else if(S == 7) k_oz_slice<7><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
