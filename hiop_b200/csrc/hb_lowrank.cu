@@ -3,6 +3,7 @@
 // hiopKKTLinSysCompressedXYcYd::computeDirections hiopKKTLinSys.cpp:585-691, compute_directions_for_full_space :218-309.
 #include "hb_common.cuh"
 #include "hb_dense.cuh"
+#include "hb_lowrank.cuh"
 #include <cstdlib>
 
 int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool aligned16, const double* d, double* C, int ldc);
@@ -317,41 +318,6 @@ __global__ void k_sub_stacked(int meq, int mineq, double* __restrict__ rhs, cons
 } // namespace
 
 // =============================================================================================================
-struct hb_lowrank
-{
-  hb_ctx* ctx = nullptr;
-  long long n = 0;
-  int meq = 0, mineq = 0, m = 0, lmax = 0, l = 0;
-  double sigma = 1.0;
-  // borrowed
-  const double *ixl = nullptr, *ixu = nullptr, *idl = nullptr, *idu = nullptr;
-  const double *J = nullptr, *St = nullptr, *Yt = nullptr;
-  const double *zl = nullptr, *sxl = nullptr, *zu = nullptr, *sxu = nullptr, *vl = nullptr, *sdl = nullptr, *vu = nullptr, *sdu = nullptr;
-  // owned
-  double *Dx = nullptr, *DhInv = nullptr, *Dd = nullptr, *Dd_inv = nullptr;
-  double* Jpack = nullptr;
-  const double** rowptr_dev = nullptr;
-  const double** rowptr_host = nullptr; // pinned
-  bool rows_aligned = false, rowptr_dirty = true;
-  double *Caug = nullptr, *SSt = nullptr, *Ld = nullptr, *Dd_sec = nullptr, *V = nullptr, *Mdir = nullptr, *U = nullptr, *Z = nullptr;
-  int *ipivV = nullptr, *ipivM = nullptr, *info = nullptr; // info[0]: V, info[1]: N chol, info[2]: M
-  double *Nmat = nullptr, *F = nullptr, *svec = nullptr, *rhs = nullptr, *dy = nullptr, *work = nullptr, *stats = nullptr;
-  double *nv1 = nullptr, *nv2 = nullptr; // n-vector scratch
-  double *p2l = nullptr, *md_partial = nullptr;
-  double *mi1 = nullptr, *mi2 = nullptr, *mi3 = nullptr; // m_ineq scratch
-  int md_grid = 0;
-  bool have_update = false, cond_valid = false, mdir_valid = false;
-  int condense_mode = -1; // -1 = auto, 0 = FP64 DMMA, 6/7/8 = INT8-slice tcgen05
-  int condense_used = 0;
-  // host staging (hb_lowrank_kkt_system_host)
-  double* hbuf[16] = {nullptr};
-  double* hJ = nullptr;
-  int last_refine = 0;
-  double last_resid = 0.0;
-  int* info_host = nullptr; // pinned 4 ints
-  double* stats_host = nullptr; // pinned 4 doubles
-};
-
 namespace {
 
 int dmalloc(double** p, size_t count)
@@ -494,6 +460,15 @@ int do_condense(hb_lowrank* k)
 
 } // namespace
 
+int hb_lr_gemv_rows(hb_lowrank* k, const double* A, int m, double beta, double* y, double alpha, const double* x)
+{
+  return gemv_rows(k, A, m, beta, y, alpha, x);
+}
+int hb_lr_gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* y, double alpha, const double* x)
+{
+  return gemv_cols(k, A, m, beta, y, alpha, x);
+}
+
 extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_ineq, int l_max, hb_lowrank** out)
 {
   HB_REQUIRE(c && out && n_local >= 0 && m_eq >= 0 && m_ineq >= 0 && l_max >= 0 && l_max <= 256, "hb_lowrank_create: bad arguments");
@@ -535,7 +510,7 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);

@@ -199,6 +199,18 @@ int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const double* ryc, co
  * res = {rx, rd, ryc, ryd, rxl, rxu, rdl, rdu, rszl, rszu, rsvl, rsvu}; dir = {x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu}
  * (HOST arrays of 12 DEVICE pointers). Residuals are not modified. */
 int hb_lowrank_compute_directions(hb_lowrank* k, const double* const* res, double* const* dir);
+/* compute_directions_w_IR (hiopKKTLinSys::compute_directions_w_IR hiopKKTLinSys.cpp:909-960): BiCGStab
+ * (hiopBiCGStabSolver::solve, src/LinAlg/hiopKrylovSolver.cpp:399-700; same recurrence, breakdown / stagnation / "more
+ * steps" rules and minimal-residual fallback) on the unreduced 12-block KKT system with hb_lowrank_compute_directions as
+ * the preconditioner and x0 = 0. res / dir as in hb_lowrank_compute_directions. tol is the RELATIVE tolerance the
+ * reference computes as min(mu*ir_outer_tol_factor, ir_outer_tol_min) (:942); maxit = ir_outer_maxit (<= 0: plain
+ * computeDirections, :914-917). info (HOST, 4 doubles, may be NULL) = {flag (0 converged, 3 stagnation, 4 breakdown,
+ * 1 iteration limit), iterations (half steps count 0.5), abs residual, rel residual}. Like the reference the step is
+ * accepted whatever the flag (:950-953), so the return value reports only engine errors. */
+int hb_lowrank_compute_directions_w_ir(hb_lowrank* k, const double* const* res, double* const* dir, double tol, int maxit, double* info);
+/* y = K x with the full (unsymmetric) 12 x 12 block KKT operator hiopMatVecKKTFullOpr::times_vec
+ * (hiopKKTLinSys.cpp:1619-1733); x, y: HOST arrays of 12 DEVICE pointers in the order of dir / res above. */
+int hb_lowrank_kkt_full_times_vec(hb_lowrank* k, const double* const* x, double* const* y);
 /* x = (B_k + D_x)^{-1} rhs  (hiopHessianLowRank::solve :495-540) */
 int hb_lowrank_hess_solve(hb_lowrank* k, const double* rhs, double* x);
 /* y = beta*y + alpha*(B_k [+ D_x]) x in the compact form (same operator as the recursive timesVecCmn :974-1059) */

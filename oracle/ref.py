@@ -40,6 +40,12 @@ def lib():
         L.ref_qn_hess_times_vec.argtypes = [ctypes.c_void_p, ctypes.c_double, dp, ctypes.c_double, dp, ctypes.c_int]
         L.ref_qn_compute_directions.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp)]
         L.ref_qn_compute_directions.restype = ctypes.c_int
+        L.ref_qn_compute_directions_w_IR.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ctypes.c_double, ctypes.c_int, dp]
+        L.ref_qn_compute_directions_w_IR.restype = ctypes.c_int
+        L.ref_qn_kkt_full_times_vec.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp)]
+        L.ref_qn_kkt_full_times_vec.restype = ctypes.c_int
+        L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
+        L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
         L.ref_symdense_factor_solve.restype = ctypes.c_int
         L.ref_vec_op.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, dp, dp, ctypes.c_double, ctypes.c_double]
@@ -182,6 +188,46 @@ class RefQn:
         rc = lib().ref_qn_compute_directions(self.h, RA, DA)
         assert rc == 0
         return dict(zip(DIR_NAMES, dout))
+
+
+    def _sizes(self):
+        return dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,
+                    sdu=self.mineq, zl=self.n, zu=self.n, vl=self.mineq, vu=self.mineq)
+
+    def compute_directions_w_ir(self, res: dict, mu: float, maxit: int = 8):
+        """hiopKKTLinSys::compute_directions_w_IR -> (directions, (flag, iter, abs_resid, rel_resid))."""
+        from .kkt_oracle import RES_NAMES, DIR_NAMES
+        sizes = self._sizes()
+        rin = [np.ascontiguousarray(res[k], dtype=np.float64) for k in RES_NAMES]
+        dout = [np.zeros(sizes[k]) for k in DIR_NAMES]
+        RA = (dp * 12)(*[a.ctypes.data_as(dp) for a in rin])
+        DA = (dp * 12)(*[a.ctypes.data_as(dp) for a in dout])
+        info = np.zeros(4)
+        rc = lib().ref_qn_compute_directions_w_IR(self.h, RA, DA, ctypes.c_double(mu), int(maxit), info.ctypes.data_as(dp))
+        assert rc == 0
+        return dict(zip(DIR_NAMES, dout)), tuple(info)
+
+    def kkt_full_times_vec(self, x: dict):
+        from .kkt_oracle import RES_NAMES, DIR_NAMES
+        sizes = self._sizes()
+        xin = [np.ascontiguousarray(x[k], dtype=np.float64) for k in DIR_NAMES]
+        yout = [np.zeros(sizes[k]) for k in DIR_NAMES]
+        XA = (dp * 12)(*[a.ctypes.data_as(dp) for a in xin])
+        YA = (dp * 12)(*[a.ctypes.data_as(dp) for a in yout])
+        rc = lib().ref_qn_kkt_full_times_vec(self.h, XA, YA)
+        assert rc == 0
+        return dict(zip(RES_NAMES, yout))
+
+
+def bicgstab_dense(A, Minv, b, tol, maxit):
+    """hiopBiCGStabSolver::solve on a dense system with a dense left preconditioner. Returns (x, (flag, iter, abs, rel))."""
+    n = b.size
+    Aa, pA = _d(A)
+    Ma, pM = _d(Minv)
+    x = np.array(b, dtype=np.float64).copy()
+    info = np.zeros(4)
+    lib().ref_bicgstab_dense(n, pA, pM, x.ctypes.data_as(dp), ctypes.c_double(tol), int(maxit), info.ctypes.data_as(dp))
+    return x, tuple(info)
 
 
 def symdense_factor_solve(M_upper, rhs=None):

@@ -25,14 +25,22 @@
 #include "hiopMatrixDenseRowMajor.hpp"
 #include "hiopMatrixSparseTriplet.hpp"
 #include "hiopPDPerturbation.hpp"
+#include "hiopVectorCompoundPD.hpp"
+#include "hiopKrylovSolver.hpp"
 #include "LinAlgFactory.hpp"
 
 #include <chrono>
+#include <iostream>
+#include <locale>
 #include <cstring>
 #include <vector>
 #include <cmath>
 
 using namespace hiop;
+
+// libstdc++ is linked statically into this .so in this image: make sure its stream/locale machinery is initialised before the
+// reference formats numbers into std::stringstream (hiopBiCGStabSolver::solve builds its convergence report that way).
+static std::ios_base::Init s_ios_init;
 
 namespace {
 
@@ -90,6 +98,7 @@ struct QnCtx
   hiopKKTLinSysLowRank* kkt;
   hiopMatrixDense *Jc, *Jd;
   hiopVector* gradf;
+  hiopPDPerturbationNull* pert = nullptr;
   int n, meq, mineq, lmax;
 };
 
@@ -123,6 +132,7 @@ void* ref_qn_create(int n, int m_eq, int m_ineq, int lmax, const double* ixl, co
 void ref_qn_destroy(void* h)
 {
   QnCtx* c = (QnCtx*)h;
+  delete c->pert;
   delete c->gradf; delete c->Jd; delete c->Jc; delete c->kkt; delete c->hess; delete c->it; delete c->nlp; delete c->iface;
   delete c;
 }
@@ -252,6 +262,96 @@ int ref_qn_compute_directions(void* h, const double* const* res, double* const* 
   get_vec(d.sxl, dir[4]); get_vec(d.sxu, dir[5]); get_vec(d.sdl, dir[6]); get_vec(d.sdu, dir[7]);
   get_vec(d.zl, dir[8]); get_vec(d.zu, dir[9]); get_vec(d.vl, dir[10]); get_vec(d.vu, dir[11]);
   return ok ? 0 : -1;
+}
+
+namespace {
+void ensure_pert(QnCtx* c)
+{
+  if(c->pert) return;
+  // the quasi-Newton driver installs the all-zero perturbation object (hiopAlgFilterIPM.cpp:1052-1059)
+  c->pert = new hiopPDPerturbationNull();
+  c->pert->initialize(c->nlp);
+  c->kkt->set_PD_perturb_calc(c->pert);
+}
+void set_resid(hiopResidual& r, const double* const* res)
+{
+  set_vec(r.rx, res[0]); set_vec(r.rd, res[1]); set_vec(r.ryc, res[2]); set_vec(r.ryd, res[3]);
+  set_vec(r.rxl, res[4]); set_vec(r.rxu, res[5]); set_vec(r.rdl, res[6]); set_vec(r.rdu, res[7]);
+  set_vec(r.rszl, res[8]); set_vec(r.rszu, res[9]); set_vec(r.rsvl, res[10]); set_vec(r.rsvu, res[11]);
+}
+void get_iter(const hiopIterate& d, double* const* dir)
+{
+  get_vec(d.x, dir[0]); get_vec(d.d, dir[1]); get_vec(d.yc, dir[2]); get_vec(d.yd, dir[3]);
+  get_vec(d.sxl, dir[4]); get_vec(d.sxu, dir[5]); get_vec(d.sdl, dir[6]); get_vec(d.sdu, dir[7]);
+  get_vec(d.zl, dir[8]); get_vec(d.zu, dir[9]); get_vec(d.vl, dir[10]); get_vec(d.vu, dir[11]);
+}
+} // namespace
+
+/// hiopKKTLinSys::compute_directions_w_IR (hiopKKTLinSys.cpp:909-960): BiCGStab on the full KKT system, preconditioned by
+/// computeDirections. mu sets the tolerance min(mu*ir_outer_tol_factor, ir_outer_tol_min); info = {flag, iter, abs, rel}.
+int ref_qn_compute_directions_w_IR(void* h, const double* const* res, double* const* dir, double mu, int maxit, double* info)
+{
+  QnCtx* c = (QnCtx*)h;
+  ensure_pert(c);
+  c->nlp->options->SetIntegerValue("ir_outer_maxit", maxit);
+  c->kkt->set_logbar_mu(mu);
+  hiopResidual r(c->nlp);
+  hiopIterate d(c->nlp);
+  set_resid(r, res);
+  bool ok = c->kkt->compute_directions_w_IR(&r, &d);
+  get_iter(d, dir);
+  if(info && c->kkt->bicgIR_) {
+    info[0] = c->kkt->bicgIR_->flag_;
+    info[1] = c->kkt->bicgIR_->get_sol_num_iter();
+    info[2] = c->kkt->bicgIR_->get_sol_abs_resid();
+    info[3] = c->kkt->bicgIR_->get_sol_rel_resid();
+  }
+  return ok ? 0 : -1;
+}
+
+/// y = K x with hiopMatVecKKTFullOpr::times_vec (hiopKKTLinSys.cpp:1619-1733); x/y in the compound order of dir/res.
+int ref_qn_kkt_full_times_vec(void* h, const double* const* x, double* const* y)
+{
+  QnCtx* c = (QnCtx*)h;
+  ensure_pert(c);
+  hiopIterate xi(c->nlp), yi(c->nlp);
+  set_vec(xi.x, x[0]); set_vec(xi.d, x[1]); set_vec(xi.yc, x[2]); set_vec(xi.yd, x[3]);
+  set_vec(xi.sxl, x[4]); set_vec(xi.sxu, x[5]); set_vec(xi.sdl, x[6]); set_vec(xi.sdu, x[7]);
+  set_vec(xi.zl, x[8]); set_vec(xi.zu, x[9]); set_vec(xi.vl, x[10]); set_vec(xi.vu, x[11]);
+  hiopVectorCompoundPD xv(&xi), yv(&yi);
+  hiopMatVecKKTFullOpr opr(c->kkt, c->it);
+  bool ok = opr.times_vec(yv, xv);
+  get_iter(yi, y);
+  return ok ? 0 : -1;
+}
+
+/// hiopBiCGStabSolver::solve (hiopKrylovSolver.cpp:399-700) on a dense n x n system A x = b with a dense left preconditioner
+/// Minv (both row-major), x0 = 0: pins the recurrence, the exit rules and the minimal-residual fallback of the restatement
+/// on systems that need many iterations. b is overwritten with the solution; info = {flag, iter, abs_resid, rel_resid}.
+int ref_bicgstab_dense(int n, const double* A, const double* Minv, double* b, double tol, int maxit, double* info)
+{
+  hiopMatrixDense* Am = LinearAlgebraFactory::create_matrix_dense("DEFAULT", n, n);
+  hiopMatrixDense* Mm = LinearAlgebraFactory::create_matrix_dense("DEFAULT", n, n);
+  memcpy(Am->local_data(), A, sizeof(double) * (size_t)n * n);
+  memcpy(Mm->local_data(), Minv, sizeof(double) * (size_t)n * n);
+  hiopMatVecOpr Aop(Am), Mop(Mm);
+  hiopVector* bv = LinearAlgebraFactory::create_vector("DEFAULT", n);
+  set_vec(bv, b);
+  bool ok;
+  {
+    hiopBiCGStabSolver solver(n, &Aop, &Mop, nullptr, nullptr);
+    solver.set_max_num_iter(maxit);
+    solver.set_tol(tol);
+    solver.set_x0(0.0);
+    ok = solver.solve(bv);
+    info[0] = solver.flag_;
+    info[1] = solver.get_sol_num_iter();
+    info[2] = solver.get_sol_abs_resid();
+    info[3] = solver.get_sol_rel_resid();
+  }
+  get_vec(bv, b);
+  delete bv; delete Mm; delete Am;
+  return ok ? 0 : 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -36,6 +36,12 @@ def qn_case(name, n, m, l, mz):
     d = q.compute_directions(p.res)
     x = np.random.default_rng(77).standard_normal(n)
     Bx = q.hess_times_vec(0.0, np.zeros(n), 1.0, x, True)
+    # outer refinement (a19): the full 12-block operator on a random compound vector, and compute_directions_w_IR
+    rng = np.random.default_rng(78)
+    kx_in = {k: rng.standard_normal(np.asarray(p.res[rk]).size) for k, rk in zip(DIR_NAMES, RES_NAMES)}
+    kx_out = q.kkt_full_times_vec(kx_in)
+    ir_mu, ir_maxit = 1e-3, 8
+    d_ir, ir_info = q.compute_directions_w_ir(p.res, ir_mu, ir_maxit)
     out = dict(n=n, m_eq=p.m_eq, m_ineq=p.m_ineq, l=l, sigma=p.sigma, Jc=p.Jc, Jd=p.Jd, ixl=p.ixl, ixu=p.ixu, idl=p.idl,
                idu=p.idu, sxl=p.sxl, sxu=p.sxu, zl=p.zl, zu=p.zu, sdl=p.sdl, sdu=p.sdu, vl=p.vl, vu=p.vu, St=p.St, Yt=p.Yt,
                L=p.L, D=p.D, rx=p.rx, ryc=p.ryc, ryd=p.ryd, tv_x=x,
@@ -45,6 +51,11 @@ def qn_case(name, n, m, l, mz):
         out["res_" + k] = p.res[k]
     for k in DIR_NAMES:
         out["ref_dir_" + k] = d[k]
+        out["ref_ir_dir_" + k] = d_ir[k]
+        out["kx_in_" + k] = kx_in[k]
+    for k in RES_NAMES:
+        out["ref_kx_out_" + k] = kx_out[k]
+    out["ir_mu"], out["ir_maxit"], out["ref_ir_info"] = ir_mu, ir_maxit, np.array(ir_info)
     q.close()
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(name, "N cond ~", np.linalg.cond(N))

@@ -64,6 +64,75 @@ def test_compute_directions_matches_reference():
     q.close()
 
 
+def test_kkt_full_operator_matches_reference():
+    """hiopMatVecKKTFullOpr::times_vec on a random 12-block vector."""
+    p = synth.make_qn_problem(700, 12, 4, masked_zero_divisors=True)
+    q = _ref_system(p)
+    Dx_r, _, _ = q.update()
+    _, st = _oracle_state(p)
+    rng = np.random.default_rng(17)
+    x = {k: rng.standard_normal(np.asarray(p.res[rk]).size) for k, rk in zip(ko.DIR_NAMES, ko.RES_NAMES)}
+    it = dict(sxl=p.sxl, sxu=p.sxu, zl=p.zl, zu=p.zu, sdl=p.sdl, sdu=p.sdu, vl=p.vl, vu=p.vu)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    y_r = q.kkt_full_times_vec(x)
+    y = ko.kkt_full_times_vec(st, it, pat, x, Dx_r)
+    for k in ko.RES_NAMES:
+        tol = 1e-12 if k in ("rx", "ryc", "ryd") else 0.0          # elementwise rows are bit-identical
+        assert np.abs(y[k] - y_r[k]).max(initial=0.0) <= tol * max(1.0, np.abs(y_r[k]).max(initial=0.0)), k
+    q.close()
+
+
+@pytest.mark.parametrize("mu,maxit", [(1e-1, 8), (1e-6, 8), (1e-3, 2), (1.0, 0)])
+def test_compute_directions_w_ir_matches_reference(mu, maxit):
+    """hiopKKTLinSys::compute_directions_w_IR: BiCGStab on the full KKT system, preconditioned by computeDirections."""
+    p = synth.make_qn_problem(1200, 16, 4, masked_zero_divisors=True)
+    q = _ref_system(p)
+    Dx_r, _, _ = q.update()
+    _, st = _oracle_state(p)
+    it = dict(sxl=p.sxl, sxu=p.sxu, zl=p.zl, zu=p.zu, sdl=p.sdl, sdu=p.sdu, vl=p.vl, vu=p.vu)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    d_r, info_r = q.compute_directions_w_ir(p.res, mu, maxit)
+    d, info = ko.compute_directions_w_ir(st, it, pat, p.res, mu, maxit, Dx=Dx_r)
+    if maxit > 0:
+        assert info[0] == info_r[0] and info[1] == info_r[1], (info, info_r)     # same exit flag, same (half-)iteration count
+    for k in ko.DIR_NAMES:
+        assert np.all(np.isfinite(d_r[k])), k
+        assert np.abs(d[k] - d_r[k]).max(initial=0.0) <= 1e-8 * max(1.0, np.abs(d_r[k]).max(initial=0.0)), k
+    # the defining property: the returned direction solves the unreduced system to the BiCGStab tolerance
+    if maxit > 0 and info_r[0] == 0:
+        y = ko.kkt_full_times_vec(st, it, pat, d, Dx_r)
+        rr = np.concatenate([y[k] - np.asarray(p.res[k]) for k in ko.RES_NAMES])
+        bb = np.concatenate([np.asarray(p.res[k]) for k in ko.RES_NAMES])
+        assert np.linalg.norm(rr) <= min(mu * 1e-2, 1e-6) * np.linalg.norm(bb) * 1.01
+    q.close()
+
+
+@pytest.mark.parametrize("case", ["good_prec", "rough_prec", "no_prec_budget", "singular", "zero_rhs"])
+def test_bicgstab_recurrence_matches_reference(case):
+    """hiopBiCGStabSolver::solve on dense systems that need several iterations / hit the non-convergence exits."""
+    rng = np.random.default_rng(21)
+    n = 60
+    A = rng.standard_normal((n, n)) + 8.0 * np.eye(n)
+    b = rng.standard_normal(n)
+    tol, maxit = 1e-10, 40
+    if case == "good_prec":
+        Minv = np.linalg.inv(A + 1e-3 * rng.standard_normal((n, n)))
+    elif case == "rough_prec":
+        Minv = np.linalg.inv(A + 0.15 * rng.standard_normal((n, n)))   # ~10 iterations; beyond that BiCGStab trajectories are rounding-chaotic
+    elif case == "no_prec_budget":
+        Minv, maxit = np.eye(n), 5                 # runs out of iterations -> minimal-residual fallback
+    elif case == "singular":
+        A = np.outer(rng.standard_normal(n), rng.standard_normal(n))   # rank 1: breakdown / stagnation exits
+        Minv = np.eye(n)
+    else:
+        Minv, b = np.eye(n), np.zeros(n)
+    x_r, info_r = ref.bicgstab_dense(A, Minv, b, tol, maxit)
+    x, flag, it, a, rel = ko.bicgstab(lambda v: A @ v, lambda v: Minv @ v, b, tol, maxit)
+    assert flag == info_r[0] and it == info_r[1], ((flag, it, a, rel), info_r)
+    assert np.abs(x - x_r).max(initial=0.0) <= 1e-7 * max(1.0, np.abs(x_r).max(initial=0.0))
+    assert abs(a - info_r[2]) <= 1e-3 * abs(info_r[2]) + 1e-13     # residual norms: same digits up to rounding amplification
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
