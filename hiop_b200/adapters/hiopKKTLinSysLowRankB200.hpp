@@ -22,6 +22,10 @@ public:
   bool update(const hiopIterate* iter, const hiopVector* grad_f, const hiopMatrixDense* Jac_c, const hiopMatrixDense* Jac_d,
               hiopHessianLowRank* Hess) override;
   bool solveCompressed(hiopVector& rx, hiopVector& ryc, hiopVector& ryd, hiopVector& dx, hiopVector& dyc, hiopVector& dyd) override;
+  /// Outer BiCGStab refinement (hiopKKTLinSys.cpp:909-960) on the device: one upload of the 12 residual blocks, one download
+  /// of the 12 direction blocks; operator, preconditioner and all reductions stay in HBM. HIOP_B200_IR=host keeps the
+  /// reference's host-side BiCGStab (which then calls solveCompressed() above for every preconditioner apply).
+  bool compute_directions_w_IR(const hiopResidual* resid, hiopIterate* direction) override;
 
 private:
   bool upload(double* dst, const double* src, size_t count);
@@ -32,5 +36,7 @@ private:
   // device mirrors
   double *dJ_, *dSt_, *dYt_;
   double *dpat_[4], *dit_[8], *drhs_[3], *dsol_[3];
+  double *dres_[12], *ddir_[12]; // allocated on the first device-side refinement
+  bool ir_on_device_;
 };
 } // namespace hiop

@@ -5,10 +5,12 @@
 #include "hiopLinSolverSymDenseLapack.hpp"
 #include "hiopNlpFormulation.hpp"
 #include "hiopIterate.hpp"
+#include "hiopResidual.hpp"
 
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 
 namespace hiop
 {
@@ -93,6 +95,9 @@ bool hiopLinSolverSymDenseB200::solve(hiopVector& x)
 hiopKKTLinSysLowRankB200::hiopKKTLinSysLowRankB200(hiopNlpFormulation* nlp)
   : hiopKKTLinSysLowRank(nlp), ctx_(shared_ctx()), h_(nullptr), dJ_(nullptr), dSt_(nullptr), dYt_(nullptr)
 {
+  for(int i = 0; i < 12; i++) dres_[i] = ddir_[i] = nullptr;
+  const char* ir = getenv("HIOP_B200_IR");
+  ir_on_device_ = !(ir && !strcmp(ir, "host"));
   n_ = nlp_->n_local();
   meq_ = nlp_->m_eq();
   mineq_ = nlp_->m_ineq();
@@ -127,6 +132,8 @@ hiopKKTLinSysLowRankB200::~hiopKKTLinSysLowRankB200()
   for(auto* p : dit_) hb_free(ctx_, p);
   for(auto* p : drhs_) hb_free(ctx_, p);
   for(auto* p : dsol_) hb_free(ctx_, p);
+  for(auto* p : dres_) if(p) hb_free(ctx_, p);
+  for(auto* p : ddir_) if(p) hb_free(ctx_, p);
 }
 
 bool hiopKKTLinSysLowRankB200::upload(double* dst, const double* src, size_t count)
@@ -187,6 +194,46 @@ bool hiopKKTLinSysLowRankB200::solveCompressed(hiopVector& rx, hiopVector& ryc, 
   // like the reference, rx is overwritten with rx - J^T [dyc;dyd] (hiopKKTLinSys.cpp:1178)
   if(n_) must(hb_memcpy_d2h(ctx_, rx.local_data(), drhs_[0], sizeof(double) * n_), "d2h");
   must(hb_ctx_sync(ctx_), "hb_ctx_sync");
+  return true;
+}
+
+bool hiopKKTLinSysLowRankB200::compute_directions_w_IR(const hiopResidual* resid, hiopIterate* dir)
+{
+  const int maxit = nlp_->options->GetInteger("ir_outer_maxit");
+  if(!ir_on_device_ || maxit <= 0) return hiopKKTLinSys::compute_directions_w_IR(resid, dir);
+  nlp_->runStats.tmSolverInternal.start();
+  // compound order of hiopVectorCompoundPD (hiopVectorCompoundPD.cpp:228-255)
+  const hiopVector* rb[12] = {resid->rx, resid->rd, resid->ryc, resid->ryd, resid->rxl, resid->rxu, resid->rdl, resid->rdu,
+                              resid->rszl, resid->rszu, resid->rsvl, resid->rsvu};
+  hiopVector* db[12] = {dir->x, dir->d, dir->yc, dir->yd, dir->sxl, dir->sxu, dir->sdl, dir->sdu, dir->zl, dir->zu, dir->vl, dir->vu};
+  for(int i = 0; i < 12; i++) {
+    const size_t sz = (size_t)rb[i]->get_size();
+    if(!dres_[i]) {
+      must(hb_malloc(ctx_, sizeof(double) * sz, (void**)&dres_[i]), "hb_malloc(residual)");
+      must(hb_malloc(ctx_, sizeof(double) * sz, (void**)&ddir_[i]), "hb_malloc(direction)");
+    }
+    upload(dres_[i], rb[i]->local_data_const(), sz);
+  }
+  const double tol = std::min(mu_ * nlp_->options->GetNumeric("ir_outer_tol_factor"), nlp_->options->GetNumeric("ir_outer_tol_min"));
+  double info[4] = {0, 0, 0, 0};
+  const int rc = hb_lowrank_compute_directions_w_ir(h_, dres_, ddir_, tol, maxit, info);
+  if(rc != HB_OK) {
+    nlp_->log->printf(hovError, "hiopKKTLinSysLowRankB200::compute_directions_w_IR: %s\n", hb_last_error());
+    nlp_->runStats.tmSolverInternal.stop();
+    return false;
+  }
+  for(int i = 0; i < 12; i++) {
+    const size_t sz = (size_t)db[i]->get_size();
+    if(sz) must(hb_memcpy_d2h(ctx_, db[i]->local_data(), ddir_[i], sizeof(double) * sz), "d2h");
+  }
+  must(hb_ctx_sync(ctx_), "hb_ctx_sync");
+  nlp_->runStats.kkt.nIterRefinInner += info[1];
+  if(info[0] != 0.0)  // the step is accepted whatever BiCGStab reports (hiopKKTLinSys.cpp:950-953)
+    nlp_->log->printf(hovWarning, "BiCGStab (device) did NOT converge: flag %d after %g iters, abs res %g, rel res %g\n", (int)info[0], info[1],
+                      info[2], info[3]);
+  else
+    nlp_->log->printf(hovScalars, "BiCGStab (device) converged: actual normResid=%g relResid=%g iter=%g\n", info[2], info[3], info[1]);
+  nlp_->runStats.tmSolverInternal.stop();
   return true;
 }
 

@@ -266,6 +266,24 @@ class KKTLinSysLowRank:
         check(rc, "hb_lowrank_compute_directions")
         return True
 
+    def compute_directions_w_IR(self, res: dict, dirs: dict, mu: float, maxit: int = 8, tol_factor: float = 1e-2, tol_min: float = 1e-6):
+        """hiopKKTLinSys::compute_directions_w_IR; tol = min(mu*ir_outer_tol_factor, ir_outer_tol_min) like the reference.
+        Returns (ok, (flag, iterations, abs_resid, rel_resid))."""
+        R = (ctypes.c_void_p * 12)(*[_ptr(res[k]) for k in RES_NAMES])
+        Dp = (ctypes.c_void_p * 12)(*[_ptr(dirs[k]) for k in DIR_NAMES])
+        info = (ctypes.c_double * 4)()
+        rc = self.ctx.L.hb_lowrank_compute_directions_w_ir(self.h, R, Dp, min(mu * tol_factor, tol_min), int(maxit), info)
+        if rc == -4:
+            return False, tuple(info)
+        check(rc, "hb_lowrank_compute_directions_w_ir")
+        return True, (int(info[0]), info[1], info[2], info[3])
+
+    def kkt_full_times_vec(self, x: dict, y: dict):
+        """y = K x, hiopMatVecKKTFullOpr::times_vec; x keyed by DIR_NAMES, y by RES_NAMES."""
+        X = (ctypes.c_void_p * 12)(*[_ptr(x[k]) for k in DIR_NAMES])
+        Y = (ctypes.c_void_p * 12)(*[_ptr(y[k]) for k in RES_NAMES])
+        check(self.ctx.L.hb_lowrank_kkt_full_times_vec(self.h, X, Y), "hb_lowrank_kkt_full_times_vec")
+
     def hess_solve(self, rhs, x):
         check(self.ctx.L.hb_lowrank_hess_solve(self.h, _ptr(rhs), _ptr(x)), "hb_lowrank_hess_solve")
 

@@ -47,6 +47,17 @@ def test_oracle_qn_against_golden(name):
         assert np.abs(d[k] - b).max() <= 1e-8 * max(1.0, np.abs(b).max()) if b.size else True, k
     Bx = ko.hess_times_vec(g["St"], g["Yt"], float(g["sigma"]), Dx, 0.0, np.zeros_like(Dx), 1.0, g["tv_x"], True)
     assert np.abs(Bx - g["ref_Bx"]).max() <= 1e-10 * np.abs(g["ref_Bx"]).max()
+    # outer refinement: full 12-block operator and compute_directions_w_IR
+    y = ko.kkt_full_times_vec(st, it, pat, {k: g["kx_in_" + k] for k in ko.DIR_NAMES}, Dx)
+    for k in ko.RES_NAMES:
+        b = g["ref_kx_out_" + k]
+        tol = 1e-12 if k in ("rx", "ryc", "ryd") else 0.0
+        assert np.abs(y[k] - b).max(initial=0.0) <= tol * max(1.0, np.abs(b).max(initial=0.0)), k
+    d, info = ko.compute_directions_w_ir(st, it, pat, res, float(g["ir_mu"]), int(g["ir_maxit"]), Dx=Dx)
+    assert info[0] == g["ref_ir_info"][0] and info[1] == g["ref_ir_info"][1]
+    for k in ko.DIR_NAMES:
+        b = g["ref_ir_dir_" + k]
+        assert np.abs(d[k] - b).max(initial=0.0) <= 1e-8 * max(1.0, np.abs(b).max(initial=0.0)), k
 
 
 def test_oracle_symdense_against_golden():

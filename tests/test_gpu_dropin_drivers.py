@@ -63,8 +63,17 @@ def _compare(exe, args, inf_du_rel=0.0):
     return worst, len(tab_r), out_b
 
 
+@pytest.fixture(params=["device", "host"])
+def ir_mode(request):
+    """Where the outer BiCGStab refinement runs: on the device (hb_lowrank_compute_directions_w_ir, the default) or in the
+    reference's host code calling the engine's solveCompressed for every preconditioner apply."""
+    os.environ["HIOP_B200_IR"] = request.param
+    yield request.param
+    os.environ.pop("HIOP_B200_IR", None)
+
+
 @pytest.mark.parametrize("args", [["500", "-selfcheck"], ["5000", "-selfcheck"], ["5000", "-unconstrained", "-selfcheck"]])
-def test_ex2_iterate_sequence(args):
+def test_ex2_iterate_sequence(args, ir_mode):
     # Constrained Ex2 drives the condensed matrix N to the edge of FP64: the REFERENCE's own solveWithRefin prints
     # "reduced residual to ONLY 7.6e-06 after 3 iterative refinements" before 22 of its 35 iterates at n=5000. The dual
     # step of such an iterate (hence the printed inf_du) carries a component from N's near-null space that depends on
@@ -80,7 +89,7 @@ def test_ex2_iterate_sequence(args):
 
 
 @pytest.mark.parametrize("args", [["500", "1.0", "-selfcheck"], ["1000", "1.0"], ["50000", "1.0", "-selfcheck"]])
-def test_ex1_iterate_sequence(args):
+def test_ex1_iterate_sequence(args, ir_mode):
     worst, nit, out = _compare("ex1_b200.exe", args)
     assert worst <= 1e-5, worst
 
