@@ -121,6 +121,9 @@ def lib() -> ctypes.CDLL:
     f("hb_lowrank_get_condense_mode", c_i, c_vp)
     f("hb_lowrank_solve_compressed", c_i, c_vp, *([c_dp] * 6))
     f("hb_lowrank_compute_directions", c_i, c_vp, P(c_vp), P(c_vp))
+    f("hb_lowrank_secant_reset", c_i, c_vp, c_d, c_i)
+    f("hb_lowrank_secant_update", c_i, c_vp, c_dp, c_dp, c_dp, c_dp, c_i, P(c_i))
+    f("hb_lowrank_secant_state", c_i, c_vp, P(c_i), P(c_d), P(c_vp), P(c_vp), c_dp, c_dp)
     f("hb_lowrank_compute_directions_w_ir", c_i, c_vp, P(c_vp), P(c_vp), c_d, c_i, P(c_d))
     f("hb_lowrank_kkt_full_times_vec", c_i, c_vp, P(c_vp), P(c_vp))
     f("hb_lowrank_hess_solve", c_i, c_vp, c_dp, c_dp)

@@ -234,6 +234,36 @@ class KKTLinSysLowRank:
                                                Lh.ctypes.data_as(ctypes.c_void_p), Dh.ctypes.data_as(ctypes.c_void_p)),
               "hb_lowrank_set_secant")
 
+    # ---- hiopHessianLowRank::update on the device: the engine owns S_t, Y_t, x_prev, grad_f_prev, J_prev ----
+    def secant_reset(self, sigma0: float = 1.0, sigma_strategy: int = 1):
+        check(self.ctx.L.hb_lowrank_secant_reset(self.h, float(sigma0), int(sigma_strategy)), "hb_lowrank_secant_reset")
+
+    def secant_update(self, x, grad_f, yc, yd, jacobian_is_constant: bool = False) -> int:
+        """Returns the status: 0 first iterate stored, 1 pair accepted, 2 / 3 skipped (see include/hiopb200.h)."""
+        st = ctypes.c_int(0)
+        check(self.ctx.L.hb_lowrank_secant_update(self.h, _ptr(x), _ptr(grad_f), _ptr(yc), _ptr(yd), int(jacobian_is_constant), ctypes.byref(st)),
+              "hb_lowrank_secant_update")
+        return st.value
+
+    def secant_state(self):
+        """(l, sigma, St, Yt, L, D) as numpy arrays (S_t, Y_t are downloaded)."""
+        l, sg = ctypes.c_int(0), ctypes.c_double(0.0)
+        pS, pY = ctypes.c_void_p(), ctypes.c_void_p()
+        lm = max(self.l_max, 1)
+        L, D = np.zeros(lm * lm), np.zeros(lm)
+        check(self.ctx.L.hb_lowrank_secant_state(self.h, ctypes.byref(l), ctypes.byref(sg), ctypes.byref(pS), ctypes.byref(pY),
+                                                 L.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), D.ctypes.data_as(ctypes.POINTER(ctypes.c_double))),
+              "hb_lowrank_secant_state")
+        ll = l.value
+        St, Yt = np.zeros((ll, self.n)), np.zeros((ll, self.n))
+        self.ctx.sync()
+        if ll and self.n:
+            nbytes = 8 * ll * self.n
+            check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, St.ctypes.data_as(ctypes.c_void_p), pS, nbytes), "d2h")
+            check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, Yt.ctypes.data_as(ctypes.c_void_p), pY, nbytes), "d2h")
+            self.ctx.sync()
+        return ll, sg.value, St, Yt, L[:ll * ll].reshape(ll, ll).copy(), D[:ll].copy()
+
     def update(self, zl, sxl, zu, sxu, vl, sdl, vu, sdu) -> bool:
         self._keep["it"] = (zl, sxl, zu, sxu, vl, sdl, vu, sdu)
         check(self.ctx.L.hb_lowrank_update(self.h, *[_ptr(t) for t in (zl, sxl, zu, sxu, vl, sdl, vu, sdu)]), "hb_lowrank_update")

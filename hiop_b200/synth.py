@@ -197,3 +197,27 @@ def make_mds_problem(nxs: int, nxd: int, neq: int, nineq: int, nnz_per_row: int 
                       idl=idl, idu=idu, sxl=U(n), sxu=U(n) * ixu, zl=U(n), zu=U(n) * ixu, sdl=U(nineq), sdu=U(nineq) * idu, vl=U(nineq),
                       vu=U(nineq) * idu, delta_wx=np.full(n, dwx), delta_wd=np.full(nineq, dwx), delta_cc=np.full(neq, dcc),
                       delta_cd=np.full(nineq, dcc), rx=r.standard_normal(n), ryc=r.standard_normal(neq), ryd=r.standard_normal(nineq))
+
+
+def make_secant_sequence(n, m_eq, m_ineq, steps=8, seed=31):
+    """Iterate sequence for hiopHessianLowRank::update: x_k, grad_f_k (= diag(a) x_k, so s^T y > 0 on regular steps), multipliers,
+    slowly varying Jacobians. Step 3 repeats the previous x (||s|| = 0 -> skipped), step 5 flips the gradient's sign against the
+    step (s^T y < 0 -> skipped)."""
+    rng = np.random.default_rng(seed)
+    a = rng.uniform(0.5, 2.0, n)
+    Jc0, Jd0 = rng.standard_normal((m_eq, n)) / np.sqrt(n), rng.standard_normal((m_ineq, n)) / np.sqrt(n)
+    seq = []
+    x = rng.standard_normal(n)
+    for k in range(steps):
+        if k == 3:
+            xk = seq[-1]["x"].copy()
+        else:
+            xk = x + 0.1 * rng.standard_normal(n)
+        x = xk
+        g = a * xk
+        if k == 5:
+            g = seq[-1]["grad_f"] - 3.0 * a * (xk - seq[-1]["x"])
+        seq.append(dict(x=xk, grad_f=g, yc=rng.standard_normal(m_eq), yd=rng.standard_normal(m_ineq),
+                        Jc=Jc0 + 1e-3 * k * rng.standard_normal((m_eq, n)) / np.sqrt(n),
+                        Jd=Jd0 + 1e-3 * k * rng.standard_normal((m_ineq, n)) / np.sqrt(n)))
+    return seq

@@ -169,6 +169,26 @@ int hb_lowrank_set_jacobian(hb_lowrank* k, const double* Jc, const double* Jd);
  * "local" DEFAULT-space objects in the reference too, hiopHessianLowRank.cpp:85-87); sigma = B0 scaling. */
 int hb_lowrank_set_secant(hb_lowrank* k, int l, double sigma, const double* St, const double* Yt, const double* L_host,
                           const double* D_host);
+/* Secant bookkeeping on the device (hiopHessianLowRank::update, hiopHessianLowRank.cpp:262-388, with growL/growD/updateL/
+ * updateD :779-867 and appendRow/shiftRows/replaceRow of hiopMatrixDenseRowMajor.cpp:129-137, 238-284). In this mode the
+ * engine OWNS S_t, Y_t, x_prev, grad_f_prev and J_prev; hb_lowrank_set_secant is not called by the host.
+ *   hb_lowrank_secant_reset: empty memory, sigma = sigma0; sigma_strategy = HB_SIGMA_* (hiopHessianLowRank.cpp:124-136).
+ *   hb_lowrank_secant_update: x, grad_f (n_local), yc, yd = the CURRENT iterate; the current Jacobian is the one registered
+ *     with hb_lowrank_set_jacobian. Forms s = x - x_prev and y = grad_f - grad_f_prev + (J - J_prev)^T [yc; yd] in one fused
+ *     pass that also refreshes J_prev, applies the reference's two skip rules (||s||_inf < 100 eps; s^T y <= ||s|| ||y||
+ *     sqrt(eps)), appends or shifts the pair into S_t / Y_t, updates L, D and sigma (clamped to [1e-8, 1e8]).
+ *     jacobian_is_constant != 0 skips the Jacobian terms (linear constraints; no J_prev is allocated).
+ *     *status: 0 first iterate stored, 1 pair accepted, 2 skipped (s too small), 3 skipped (s^T y not positive enough).
+ *   hb_lowrank_secant_state: l, sigma, device pointers of S_t / Y_t (l x n_local row-major), HOST copies of L (l x l) and D. */
+#define HB_SIGMA_STY 1
+#define HB_SIGMA_STY_INV 2
+#define HB_SIGMA_SNRM_YNRM 3
+#define HB_SIGMA_STY_SNRM_YNRM 4
+#define HB_SIGMA_CONSTANT 5
+int hb_lowrank_secant_reset(hb_lowrank* k, double sigma0, int sigma_strategy);
+int hb_lowrank_secant_update(hb_lowrank* k, const double* x, const double* grad_f, const double* yc, const double* yd,
+                             int jacobian_is_constant, int* status);
+int hb_lowrank_secant_state(hb_lowrank* k, int* l, double* sigma, const double** St, const double** Yt, double* L_host, double* D_host);
 /* update(): Dx = zl/sxl|ixl + zu/sxu|ixu, DhInv = 1/(sigma+Dx), Dd = vl/sdl|idl + vu/sdu|idu, Dd_inv = 1/Dd in ONE fused
  * pass (hiopKKTLinSys.cpp:1057-1094 + hiopHessianLowRank.cpp:221-233; 7 n-passes in the reference). Borrows the
  * iterate pointers until the next update (they are read again by hb_lowrank_compute_directions). */

@@ -44,6 +44,10 @@ def lib():
         L.ref_qn_compute_directions_w_IR.restype = ctypes.c_int
         L.ref_qn_kkt_full_times_vec.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp)]
         L.ref_qn_kkt_full_times_vec.restype = ctypes.c_int
+        L.ref_qn_hess_update.argtypes = [ctypes.c_void_p, dp, dp, dp, dp, dp, dp, ctypes.POINTER(ctypes.c_int), dp, dp, dp, dp, dp]
+        L.ref_qn_hess_update.restype = ctypes.c_int
+        L.ref_qn_set_sigma_strategy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+        L.ref_qn_set_sigma_strategy.restype = None
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -189,6 +193,23 @@ class RefQn:
         assert rc == 0
         return dict(zip(DIR_NAMES, dout))
 
+
+    def hess_update(self, x, grad_f, yc, yd, Jc, Jd):
+        """hiopHessianLowRank::update -> (l, St[l x n], Yt[l x n], L[l x l], D[l], sigma) after the call."""
+        lm = max(self.lmax, 1)
+        St, Yt = np.zeros((lm, self.n)), np.zeros((lm, self.n))
+        L, D = np.zeros(lm * lm), np.zeros(lm)
+        l = ctypes.c_int(0)
+        sg = np.zeros(1)
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (x, grad_f, yc, yd, Jc, Jd)]
+        rc = lib().ref_qn_hess_update(self.h, *[v.ctypes.data_as(dp) for v in a], ctypes.byref(l), St.ctypes.data_as(dp), Yt.ctypes.data_as(dp),
+                                      L.ctypes.data_as(dp), D.ctypes.data_as(dp), sg.ctypes.data_as(dp))
+        assert rc == 0
+        ll = l.value
+        return ll, St[:ll].copy(), Yt[:ll].copy(), L[:ll * ll].reshape(ll, ll).copy(), D[:ll].copy(), float(sg[0])
+
+    def set_sigma_strategy(self, strategy: int, sigma0: float = 1.0):
+        lib().ref_qn_set_sigma_strategy(self.h, int(strategy), ctypes.c_double(sigma0))
 
     def _sizes(self):
         return dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,

@@ -264,6 +264,40 @@ int ref_qn_compute_directions(void* h, const double* const* res, double* const* 
   return ok ? 0 : -1;
 }
 
+/// hiopHessianLowRank::update (hiopHessianLowRank.cpp:262-388) with the iterate (x, yc, yd), grad_f and the Jacobians given as
+/// plain arrays. Reads back the secant memory afterwards: out_l = rows of S_t/Y_t; St, Yt (lmax x n, first out_l rows valid),
+/// L (lmax x lmax row-major, leading out_l x out_l block valid, packed with stride out_l), D (out_l), sigma.
+int ref_qn_hess_update(void* h, const double* x, const double* grad_f, const double* yc, const double* yd, const double* Jc, const double* Jd,
+                       int* out_l, double* St, double* Yt, double* L, double* D, double* sigma)
+{
+  QnCtx* c = (QnCtx*)h;
+  set_vec(c->it->x, x); set_vec(c->it->yc, yc); set_vec(c->it->yd, yd);
+  set_vec(c->gradf, grad_f);
+  ref_qn_set_jac(h, Jc, Jd);
+  bool ok = c->hess->update(*c->it, *c->gradf, *c->Jc, *c->Jd);
+  hiopHessianLowRank* H = c->hess;
+  const int l = H->St_->m();
+  *out_l = l;
+  *sigma = H->sigma;
+  if(l > 0) {
+    memcpy(St, H->St_->local_data_const(), sizeof(double) * (size_t)l * c->n);
+    memcpy(Yt, H->Yt_->local_data_const(), sizeof(double) * (size_t)l * c->n);
+    memcpy(L, H->L_->local_data_const(), sizeof(double) * l * l);
+    memcpy(D, H->D_->local_data_const(), sizeof(double) * l);
+  }
+  return ok ? 0 : -1;
+}
+
+/// sigma_update_strategy 1..5 = sty, sty_inv, snrm_ynrm, sty_srnm_ynrm, sigma0 (hiopHessianLowRank.cpp:49-53, 124-136); also
+/// resets sigma to sigma0 like the constructor does (:120-121).
+void ref_qn_set_sigma_strategy(void* h, int strategy, double sigma0)
+{
+  QnCtx* c = (QnCtx*)h;
+  c->hess->sigma_update_strategy = strategy;
+  c->hess->sigma0 = sigma0;
+  c->hess->sigma = sigma0;
+}
+
 namespace {
 void ensure_pert(QnCtx* c)
 {

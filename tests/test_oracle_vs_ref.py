@@ -133,6 +133,29 @@ def test_bicgstab_recurrence_matches_reference(case):
     assert abs(a - info_r[2]) <= 1e-3 * abs(info_r[2]) + 1e-13     # residual norms: same digits up to rounding amplification
 
 
+@pytest.mark.parametrize("strategy", [1, 2, 3, 4, 5])
+def test_secant_update_matches_reference(strategy):
+    """hiopHessianLowRank::update over a sequence: first call, appends, shifts (l_max = 3), both skip rules, all sigma rules."""
+    n, me, mi, lmax = 300, 4, 3, 3
+    seq = synth.make_secant_sequence(n, me, mi, steps=8)
+    ones = np.ones(n)
+    q = ref.RefQn(n, me, mi, lmax, ones, np.zeros(n), np.ones(mi), np.zeros(mi))
+    q.set_sigma_strategy(strategy, 1.0)
+    mem = ko.SecantMemory(n, lmax, 1.0, strategy)
+    statuses = []
+    for it in seq:
+        l, St, Yt, L, D, sigma = q.hess_update(it["x"], it["grad_f"], it["yc"], it["yd"], it["Jc"], it["Jd"])
+        statuses.append(mem.update(it["x"], it["grad_f"], it["yc"], it["yd"], it["Jc"], it["Jd"]))
+        assert mem.St.shape[0] == l
+        np.testing.assert_array_equal(mem.St, St)                       # s = x - x_prev: one rounding, same bits
+        assert np.abs(mem.Yt - Yt).max(initial=0.0) <= 1e-13 * max(1.0, np.abs(Yt).max(initial=0.0))
+        assert np.abs(np.tril(mem.L, -1) - np.tril(L, -1)).max(initial=0.0) <= 1e-12
+        assert np.abs(mem.D - D).max(initial=0.0) <= 1e-12
+        assert abs(mem.sigma - sigma) <= 1e-12 * sigma
+    assert statuses == [0, 1, 1, 2, 1, 3, 1, 1], statuses
+    q.close()
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
