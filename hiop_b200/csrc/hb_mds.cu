@@ -345,3 +345,118 @@ extern "C" int hb_mds_solve_compressed(hb_mds* h, hb_symdense* s, const double* 
   }
   return HB_OK;
 }
+
+// =====================================================================================================================
+// Dense-Newton KKT classes: hiopKKTLinSysDenseXYcYd / hiopKKTLinSysDenseXDYcYd
+// src/Optimization/hiopKKTLinSysDense.hpp:85-207, 249-370. Same addition order per entry as the reference's sequence of
+// addUpperTriangle / transAdd / addSubDiagonal calls -> bit-identical upper triangle; the lower triangle is zero like after
+// the reference's Msys.setToZero().
+// =====================================================================================================================
+namespace {
+
+// Dd = vl/sdl|idl + vu/sdu|idu (hiopKKTLinSys.cpp:799-803);  form 0 stores 1/(delta_wd + Dd) instead (hiopKKTLinSysDense.hpp:142-149)
+__global__ void k_dense_dd(int nineq, int form, const double* __restrict__ dwd, const double* __restrict__ vl, const double* __restrict__ sdl,
+                           const double* __restrict__ vu, const double* __restrict__ sdu, const double* __restrict__ idl, const double* __restrict__ idu,
+                           double* __restrict__ out)
+{
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < nineq; i += gridDim.x * blockDim.x) {
+    double d = form == 0 ? dwd[i] : 0.0;
+    if(idl[i] == 1.0) d = __dadd_rn(d, __ddiv_rn(vl[i], sdl[i]));
+    if(idu[i] == 1.0) d = __dadd_rn(d, __ddiv_rn(vu[i], sdu[i]));
+    out[i] = form == 0 ? __ddiv_rn(1.0, d) : d;
+  }
+}
+
+__global__ void __launch_bounds__(T)
+k_densekkt_build(int form, int nx, int neq, int nineq, const double* __restrict__ H, const double* __restrict__ Jc, const double* __restrict__ Jd,
+                 const double* __restrict__ Dx, const double* __restrict__ dwx, const double* __restrict__ dwd, const double* __restrict__ dcd,
+                 const double* __restrict__ Dd, double* __restrict__ M)
+{
+  const int N = nx + neq + nineq + (form ? nineq : 0);
+  const long long total = (long long)N * N;
+  const int yc0 = nx + (form ? nineq : 0), yd0 = yc0 + neq;
+  for(long long e = (long long)blockIdx.x * T + threadIdx.x; e < total; e += (long long)gridDim.x * T) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    double v = 0.0;
+    if(j >= i) {
+      if(i < nx) {
+        if(j < nx) {
+          v = H[(size_t)i * nx + j];
+          if(i == j) v = __dadd_rn(__dadd_rn(v, Dx[i]), dwx[i]);
+        } else if(j >= yc0 && j < yd0) {
+          v = Jc[(size_t)(j - yc0) * nx + i];
+        } else if(j >= yd0) {
+          v = Jd[(size_t)(j - yd0) * nx + i];
+        }
+      } else if(form == 0) {
+        if(i == j) {
+          if(i >= yd0) v = __dadd_rn(0.0, -Dd[i - yd0]);                                 // addSubDiagonal(-1, nx+neq, Dd_inv)      :151-152
+          if(i < nx + nineq) v = __dadd_rn(v, -dcd[i - nx]);               // addSubDiagonal(-1, nx, delta_cd)        :157 (starts at nx)
+        }
+      } else {
+        if(i == j) {
+          if(i < yc0) v = __dadd_rn(Dd[i - nx], dwd[i - nx]);              // Dd + delta_wd                            :293-294
+          else if(i < yc0 + nineq) v = __dadd_rn(0.0, -dcd[i - yc0]);                     // addSubDiagonal(-1, nx+nineq, delta_cd)  :312
+        } else if(i < yc0 && j >= yd0 && j - yd0 == i - nx) {
+          v = -1.0;                                                        // the -I block                            :296-305
+        }
+      }
+    }
+    M[e] = v;
+  }
+}
+
+} // namespace
+
+extern "C" int hb_densekkt_build(hb_ctx* c, int form, int nx, int neq, int nineq, const double* H, const double* Jc, const double* Jd,
+                                 const double* zl, const double* sxl, const double* zu, const double* sxu, const double* ixl, const double* ixu,
+                                 const double* vl, const double* sdl, const double* vu, const double* sdu, const double* idl, const double* idu,
+                                 const double* delta_wx, const double* delta_wd, const double* delta_cc, const double* delta_cd, double* Dx,
+                                 double* Dd, double* Msys)
+{
+  (void)delta_cc; // the reference reads it but never adds it in these two classes (hiopKKTLinSysDense.hpp:157, 312 use delta_cd)
+  HB_REQUIRE(c && (form == 0 || form == 1) && nx >= 0 && neq >= 0 && nineq >= 0, "hb_densekkt_build: bad arguments");
+  HB_REQUIRE(nx == 0 || (H && zl && sxl && zu && sxu && ixl && ixu && delta_wx && Dx), "hb_densekkt_build: null x block");
+  HB_REQUIRE(nineq == 0 || (Jd && vl && sdl && vu && sdu && idl && idu && delta_wd && delta_cd && Dd), "hb_densekkt_build: null d block");
+  HB_REQUIRE((neq == 0 || Jc) && Msys, "hb_densekkt_build: null argument");
+  HB_CUDA(cudaSetDevice(c->device));
+  if(nx) {
+    k_mds_update<<<grid1(c, nx), T, 0, c->stream>>>(nx, zl, sxl, zu, sxu, ixl, ixu, Dx);
+    HB_LAUNCHED();
+  }
+  if(nineq) {
+    k_dense_dd<<<grid1(c, nineq), T, 0, c->stream>>>(nineq, form, delta_wd, vl, sdl, vu, sdu, idl, idu, Dd);
+    HB_LAUNCHED();
+  }
+  const long long N = nx + neq + nineq + (form ? nineq : 0);
+  if(N) {
+    k_densekkt_build<<<grid1(c, N * N), T, 0, c->stream>>>(form, nx, neq, nineq, H, Jc, Jd, Dx, delta_wx, delta_wd, delta_cd, Dd, Msys);
+    HB_LAUNCHED();
+  }
+  return HB_OK;
+}
+
+extern "C" int hb_densekkt_solve_compressed(hb_ctx* c, hb_symdense* s, int form, int nx, int neq, int nineq, const double* rx, const double* rd,
+                                            const double* ryc, const double* ryd, double* dx, double* dd, double* dyc, double* dyd, double* work)
+{
+  HB_REQUIRE(c && s && work && (form == 0 || form == 1), "hb_densekkt_solve_compressed: bad arguments");
+  HB_REQUIRE(form == 0 || nineq == 0 || (rd && dd), "hb_densekkt_solve_compressed: XDYcYd needs rd / dd");
+  // rhs = [rx; (rd); ryc; ryd] -> solve in place -> split                                  hiopKKTLinSysDense.hpp:174-207, 332-370
+  const size_t B = sizeof(double);
+  const int o_d = nx, o_yc = nx + (form ? nineq : 0), o_yd = o_yc + neq;
+  auto cp = [&](double* dst, const double* src, int n) -> int {
+    if(n) HB_CUDA(cudaMemcpyAsync(dst, src, B * n, cudaMemcpyDeviceToDevice, c->stream));
+    return HB_OK;
+  };
+  HB_CHECK(cp(work, rx, nx));
+  if(form) HB_CHECK(cp(work + o_d, rd, nineq));
+  HB_CHECK(cp(work + o_yc, ryc, neq));
+  HB_CHECK(cp(work + o_yd, ryd, nineq));
+  const int rc = hb_symdense_solve(s, work, 1);
+  if(rc != 1) return rc < 0 ? rc : hb_fail(HB_ERR_NUMERIC, "hb_densekkt_solve_compressed: dense solve failed%s", "");
+  HB_CHECK(cp(dx, work, nx));
+  if(form) HB_CHECK(cp(dd, work + o_d, nineq));
+  HB_CHECK(cp(dyc, work + o_yc, neq));
+  HB_CHECK(cp(dyd, work + o_yd, nineq));
+  return HB_OK;
+}

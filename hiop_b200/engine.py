@@ -408,3 +408,45 @@ class KKTLinSysCompressedMDSXYcYd:
         check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self.linSys._mptr), 8 * N * N), "memcpy")
         self.ctx.sync()
         return out.reshape(N, N)
+
+
+class KKTLinSysDense:
+    """hiopKKTLinSysDenseXYcYd (form="XYcYd") / hiopKKTLinSysDenseXDYcYd (form="XDYcYd"), src/Optimization/hiopKKTLinSysDense.hpp:
+    the whole (nx + duals)^2 Newton KKT matrix assembled and factorized on the device (B1 solver)."""
+
+    def __init__(self, ctx: Context, nx: int, neq: int, nineq: int, form: str = "XYcYd", mode: int = _lib.HB_FACT_BUNCH_KAUFMAN):
+        assert form in ("XYcYd", "XDYcYd")
+        self.ctx, self.nx, self.neq, self.nineq = ctx, nx, neq, nineq
+        self.form = 0 if form == "XYcYd" else 1
+        self.N = nx + neq + nineq + (nineq if self.form else 0)
+        self.linSys = LinSolverSymDense(ctx, self.N, mode)          # owns sysMatrix(); build_kkt_matrix fills it in place
+        self.Dx, self.Dd, self.work = ctx.zeros(nx), ctx.zeros(nineq), ctx.zeros(self.N)
+
+    def close(self):
+        self.linSys.close()
+
+    def build_kkt_matrix(self, H, Jc, Jd, it: dict, pat: dict, deltas):
+        dwx, dwd, dcc, dcd = deltas
+        check(self.ctx.L.hb_densekkt_build(self.ctx.h, self.form, self.nx, self.neq, self.nineq, _ptr(H), _ptr(Jc), _ptr(Jd), _ptr(it["zl"]),
+                                           _ptr(it["sxl"]), _ptr(it["zu"]), _ptr(it["sxu"]), _ptr(pat["ixl"]), _ptr(pat["ixu"]), _ptr(it["vl"]),
+                                           _ptr(it["sdl"]), _ptr(it["vu"]), _ptr(it["sdu"]), _ptr(pat["idl"]), _ptr(pat["idu"]), _ptr(dwx), _ptr(dwd),
+                                           _ptr(dcc), _ptr(dcd), _ptr(self.Dx), _ptr(self.Dd), ctypes.c_void_p(self.linSys._mptr)), "hb_densekkt_build")
+
+    def Msys(self) -> np.ndarray:
+        out = np.zeros((self.N, self.N))
+        self.ctx.sync()
+        check(self.ctx.L.hb_memcpy_d2h(self.ctx.h, out.ctypes.data_as(ctypes.c_void_p), ctypes.c_void_p(self.linSys._mptr), 8 * self.N * self.N), "memcpy")
+        self.ctx.sync()
+        return out
+
+    def factorize(self) -> int:
+        """matrixChanged(): number of negative eigenvalues, -1 if singular."""
+        return self.linSys.matrixChanged()
+
+    def solveCompressed(self, rx, rd, ryc, ryd, dx, dd, dyc, dyd) -> bool:
+        rc = self.ctx.L.hb_densekkt_solve_compressed(self.ctx.h, self.linSys.h, self.form, self.nx, self.neq, self.nineq, _ptr(rx), _ptr(rd), _ptr(ryc),
+                                                     _ptr(ryd), _ptr(dx), _ptr(dd), _ptr(dyc), _ptr(dyd), _ptr(self.work))
+        if rc == -4:
+            return False
+        check(rc, "hb_densekkt_solve_compressed")
+        return True

@@ -281,6 +281,20 @@ int hb_mds_hxs_inertia(hb_mds* h, int* n_neg, int* n_zero);
 /* solveCompressed() (:307-403) around s (already factorized with hb_symdense_matrix_changed). rx has nxs+nxd entries. */
 int hb_mds_solve_compressed(hb_mds* h, hb_symdense* s, const double* rx, const double* ryc, const double* ryd, double* dx, double* dyc,
                             double* dyd);
+/* ---- dense-Newton KKT classes hiopKKTLinSysDenseXYcYd (form 0) / hiopKKTLinSysDenseXDYcYd (form 1) ----
+ * build_kkt_matrix (src/Optimization/hiopKKTLinSysDense.hpp:85-172, 249-330): fills Msys (N x N row-major, upper triangle;
+ * N = nx+neq+nineq, resp. nx+2*nineq+neq) with [H+Dx+dwx, Jc^T, Jd^T; 0; -Dd^{-1}] resp. [H+Dx+dwx, 0, Jc^T, Jd^T; Dd+dwd, 0, -I;
+ * ...]. Dx = zl/sxl|ixl + zu/sxu|ixu and Dd (form 1) or Dd_inv = 1/(dwd + vl/sdl|idl + vu/sdu|idu) (form 0) are computed
+ * like update() does and returned in the caller's Dx (nx) / Dd (nineq) buffers. As in the reference, delta_cd is subtracted
+ * from the nineq diagonal entries starting at the FIRST dual row (:157, :312) and delta_cc is not used.
+ * solveCompressed (:174-207, :332-370): stack the blocks, hb_symdense_solve, split. work: N doubles. rd/dd: form 1 only. */
+int hb_densekkt_build(hb_ctx* ctx, int form, int nx, int neq, int nineq, const double* H, const double* Jc, const double* Jd,
+                      const double* zl, const double* sxl, const double* zu, const double* sxu, const double* ixl, const double* ixu,
+                      const double* vl, const double* sdl, const double* vu, const double* sdu, const double* idl, const double* idu,
+                      const double* delta_wx, const double* delta_wd, const double* delta_cc, const double* delta_cd, double* Dx,
+                      double* Dd, double* Msys);
+int hb_densekkt_solve_compressed(hb_ctx* ctx, hb_symdense* s, int form, int nx, int neq, int nineq, const double* rx, const double* rd,
+                                 const double* ryc, const double* ryd, double* dx, double* dd, double* dyc, double* dyd, double* work);
 const double* hb_mds_Dx(hb_mds* h);
 const double* hb_mds_Hxs(hb_mds* h);
 const double* hb_mds_Dd_inv(hb_mds* h);

@@ -48,6 +48,8 @@ def lib():
         L.ref_qn_hess_update.restype = ctypes.c_int
         L.ref_qn_set_sigma_strategy.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
         L.ref_qn_set_sigma_strategy.restype = None
+        L.ref_densekkt_build.argtypes = [ctypes.c_int] * 4 + [dp] * 15 + [ctypes.POINTER(dp), dp]
+        L.ref_densekkt_build.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -238,6 +240,22 @@ class RefQn:
         rc = lib().ref_qn_kkt_full_times_vec(self.h, XA, YA)
         assert rc == 0
         return dict(zip(RES_NAMES, yout))
+
+
+def densekkt_build(form, H, Jc, Jd, it, pat, deltas):
+    """hiopKKTLinSysDenseXYcYd / XDYcYd::build_kkt_matrix through the reference's own classes. Returns Msys (N x N)."""
+    nx, neq, nineq = H.shape[0], Jc.shape[0], Jd.shape[0]
+    N = nx + neq + nineq + (nineq if form else 0)
+    keep = [np.ascontiguousarray(v, dtype=np.float64) for v in
+            (H, Jc if neq else np.zeros(1), Jd if nineq else np.zeros(1), pat["ixl"], pat["ixu"], pat["idl"] if nineq else np.zeros(1),
+             pat["idu"] if nineq else np.zeros(1), it["zl"], it["sxl"], it["zu"], it["sxu"], it["vl"] if nineq else np.zeros(1),
+             it["sdl"] if nineq else np.zeros(1), it["vu"] if nineq else np.zeros(1), it["sdu"] if nineq else np.zeros(1))]
+    dl = [np.ascontiguousarray(d if d.size else np.zeros(1), dtype=np.float64) for d in deltas]
+    DA = (dp * 4)(*[a.ctypes.data_as(dp) for a in dl])
+    M = np.zeros((N, N))
+    n_ret = lib().ref_densekkt_build(form, nx, neq, nineq, *[a.ctypes.data_as(dp) for a in keep], DA, M.ctypes.data_as(dp))
+    assert n_ret == N
+    return M
 
 
 def bicgstab_dense(A, Minv, b, tol, maxit):

@@ -27,6 +27,7 @@
 #include "hiopPDPerturbation.hpp"
 #include "hiopVectorCompoundPD.hpp"
 #include "hiopKrylovSolver.hpp"
+#include "hiopKKTLinSysDense.hpp"
 #include "LinAlgFactory.hpp"
 
 #include <chrono>
@@ -386,6 +387,63 @@ int ref_bicgstab_dense(int n, const double* A, const double* Minv, double* b, do
   get_vec(bv, b);
   delete bv; delete Mm; delete Am;
   return ok ? 0 : 1;
+}
+
+/// hiopKKTLinSysDenseXYcYd / XDYcYd::build_kkt_matrix (hiopKKTLinSysDense.hpp:85-172, 249-330) on plain arrays.
+/// form 0 = XYcYd (N = nx+neq+nineq), 1 = XDYcYd (N = nx+neq+2 nineq). H is nx x nx row-major (upper triangle used).
+/// deltas = {delta_wx (nx), delta_wd (nineq), delta_cc (neq), delta_cd (nineq)}. Mout is N x N row-major (upper triangle valid).
+int ref_densekkt_build(int form, int nx, int neq, int nineq, const double* H, const double* Jc, const double* Jd, const double* ixl,
+                       const double* ixu, const double* idl, const double* idu, const double* zl, const double* sxl, const double* zu,
+                       const double* sxu, const double* vl, const double* sdl, const double* vu, const double* sdu, const double* const* deltas,
+                       double* Mout)
+{
+  SynthDenseCons iface(nx, neq, nineq, ixl, ixu, idl, idu);
+  hiopNlpDenseConstraints nlp(iface);
+  nlp.options->SetIntegerValue("verbosity_level", 0);
+  nlp.options->SetStringValue("fixed_var", "relax");
+  nlp.finalizeInitialization();
+  hiopIterate it(&nlp);
+  set_vec(it.zl, zl); set_vec(it.sxl, sxl); set_vec(it.zu, zu); set_vec(it.sxu, sxu);
+  set_vec(it.vl, vl); set_vec(it.sdl, sdl); set_vec(it.vu, vu); set_vec(it.sdu, sdu);
+  hiopMatrixDense* Hm = LinearAlgebraFactory::create_matrix_dense("DEFAULT", nx, nx);
+  memcpy(Hm->local_data(), H, sizeof(double) * (size_t)nx * nx);
+  hiopMatrixDense* Jcm = nlp.alloc_Jac_c();
+  hiopMatrixDense* Jdm = nlp.alloc_Jac_d();
+  if(neq) memcpy(Jcm->local_data(), Jc, sizeof(double) * (size_t)neq * nx);
+  if(nineq) memcpy(Jdm->local_data(), Jd, sizeof(double) * (size_t)nineq * nx);
+  hiopPDPerturbationNull pert;
+  pert.initialize(&nlp);
+  set_vec(pert.delta_wx_curr_, deltas[0]); set_vec(pert.delta_wd_curr_, deltas[1]);
+  set_vec(pert.delta_cc_curr_, deltas[2]); set_vec(pert.delta_cd_curr_, deltas[3]);
+  auto fill = [&](hiopKKTLinSysCompressed* kkt) {
+    kkt->iter_ = &it; kkt->Hess_ = Hm; kkt->Jac_c_ = Jcm; kkt->Jac_d_ = Jdm;
+    kkt->set_PD_perturb_calc(&pert);
+    // the barrier diagonals as update() computes them (hiopKKTLinSys.cpp:560-566, 793-803)
+    kkt->Dx_->setToZero();
+    kkt->Dx_->axdzpy_w_pattern(1.0, *it.zl, *it.sxl, nlp.get_ixl());
+    kkt->Dx_->axdzpy_w_pattern(1.0, *it.zu, *it.sxu, nlp.get_ixu());
+  };
+  int N;
+  if(form == 0) {
+    hiopKKTLinSysDenseXYcYd kkt(&nlp);
+    fill(&kkt);
+    kkt.build_kkt_matrix(pert);
+    hiopMatrixDense& M = dynamic_cast<hiopLinSolverSymDense*>(kkt.linSys_)->sysMatrix();
+    N = M.m();
+    memcpy(Mout, M.local_data(), sizeof(double) * (size_t)N * N);
+  } else {
+    hiopKKTLinSysDenseXDYcYd kkt(&nlp);
+    fill(&kkt);
+    kkt.Dd_->setToZero();
+    kkt.Dd_->axdzpy_w_pattern(1.0, *it.vl, *it.sdl, nlp.get_idl());
+    kkt.Dd_->axdzpy_w_pattern(1.0, *it.vu, *it.sdu, nlp.get_idu());
+    kkt.build_kkt_matrix(pert);
+    hiopMatrixDense& M = dynamic_cast<hiopLinSolverSymDense*>(kkt.linSys_)->sysMatrix();
+    N = M.m();
+    memcpy(Mout, M.local_data(), sizeof(double) * (size_t)N * N);
+  }
+  delete Jdm; delete Jcm; delete Hm;
+  return N;
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -61,6 +61,23 @@ def qn_case(name, n, m, l, mz):
     print(name, "N cond ~", np.linalg.cond(N))
 
 
+def densekkt_case():
+    """hiopKKTLinSysDenseXYcYd / XDYcYd::build_kkt_matrix + LAPACK solve, nx=30, neq=7, nineq=11, non-zero regularisations."""
+    p = synth.make_mds_problem(0, 30, 7, 11, seed=19, dwx=1e-4, dcc=1e-8)
+    it = dict(zl=p.zl, sxl=p.sxl, zu=p.zu, sxu=p.sxu, vl=p.vl, sdl=p.sdl, vu=p.vu, sdu=p.sdu)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    deltas = (p.delta_wx, p.delta_wd, p.delta_cc, p.delta_cd)
+    out = dict(nx=30, neq=7, nineq=11, H=p.Hd, Jc=p.Jcd, Jd=p.Jdd, dwx=p.delta_wx, dwd=p.delta_wd, dcc=p.delta_cc, dcd=p.delta_cd, **it, **pat)
+    rng = np.random.default_rng(20)
+    for form in (0, 1):
+        M = ref.densekkt_build(form, p.Hd, p.Jcd, p.Jdd, it, pat, deltas)
+        rhs = rng.standard_normal(M.shape[0])
+        ret, sol, _, _ = ref.symdense_factor_solve(M, rhs)
+        out[f"ref_M{form}"], out[f"rhs{form}"], out[f"ref_ret{form}"], out[f"ref_sol{form}"] = M, rhs, ret, sol
+    np.savez_compressed(os.path.join(OUT, "densekkt_nx30.npz"), **out)
+    print("densekkt rets", int(out["ref_ret0"]), int(out["ref_ret1"]))
+
+
 def symdense_cases():
     out = {}
     for i, (nx, m) in enumerate([(24, 9), (70, 30), (3, 0), (1, 1), (130, 61)]):
@@ -142,5 +159,6 @@ if __name__ == "__main__":
     for c in QN_CASES:
         qn_case(*c)
     symdense_cases()
+    densekkt_case()
     vec_cases()
     mds_case()

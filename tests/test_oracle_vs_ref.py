@@ -156,6 +156,20 @@ def test_secant_update_matches_reference(strategy):
     q.close()
 
 
+@pytest.mark.parametrize("form", [0, 1])
+@pytest.mark.parametrize("nx,neq,nineq,dw,dc", [(40, 6, 9, 0.0, 0.0), (25, 10, 4, 1e-4, 1e-8), (12, 0, 5, 1e-3, 1e-6), (9, 3, 0, 0.0, 0.0)])
+def test_dense_newton_kkt_matrix_matches_reference(form, nx, neq, nineq, dw, dc):
+    """hiopKKTLinSysDenseXYcYd / XDYcYd::build_kkt_matrix incl. non-zero regularisations (delta_cd lands on the first dual
+    rows in the reference: reproduced)."""
+    p = synth.make_mds_problem(0, nx, neq, nineq, seed=7 + nx, dwx=dw, dcc=dc)
+    it = dict(zl=p.zl, sxl=p.sxl, zu=p.zu, sxu=p.sxu, vl=p.vl, sdl=p.sdl, vu=p.vu, sdu=p.sdu)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    deltas = (p.delta_wx, p.delta_wd, p.delta_cc, p.delta_cd)
+    M_r = ref.densekkt_build(form, p.Hd, p.Jcd, p.Jdd, it, pat, deltas)
+    M, _, _ = ko.dense_build_kkt_matrix(form, p.Hd, p.Jcd, p.Jdd, it, pat, deltas)
+    np.testing.assert_array_equal(M, M_r)          # same additions in the same order: bit-identical, lower triangle zero
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
