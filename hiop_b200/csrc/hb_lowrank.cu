@@ -469,6 +469,7 @@ int hb_lr_gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* 
   return gemv_cols(k, A, m, beta, y, alpha, x);
 }
 int hb_lr_multidot(hb_lowrank* k, const double* w, const double* x, double sigma_s) { return multidot(k, w, x, sigma_s); }
+int hb_lr_refresh_rowptr(hb_lowrank* k) { return refresh_rowptr(k); }
 
 extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_ineq, int l_max, hb_lowrank** out)
 {
@@ -511,7 +512,7 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);

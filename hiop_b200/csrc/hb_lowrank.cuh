@@ -41,6 +41,7 @@ struct hb_lowrank
   // secant memory owned by the engine (hb_secant.cu): S_t, Y_t (lmax x n), previous iterate / gradient / Jacobian
   double *sec_S = nullptr, *sec_Y = nullptr, *sec_xprev = nullptr, *sec_gprev = nullptr, *sec_Jprev = nullptr;
   double sec_L[64 * 64] = {0}, sec_D[64] = {0}; // host copies of L (row-major, stride l) and D; lmax <= 64 in this mode
+  double* lsq_M = nullptr; // m x m LSQ matrix / Cholesky factor + 2 m-vectors (hb_lsq.cu)
   int sec_lcurr = -1, sec_strategy = 1;
   double sec_sigma0 = 1.0;
 };
@@ -52,3 +53,5 @@ int hb_lr_gemv_rows(hb_lowrank* k, const double* A, int m, double beta, double* 
 int hb_lr_gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* y, double alpha, const double* x);
 // k->p2l (device, 2l doubles) = [sigma_s * S (w.*x); Y (w.*x)], all-reduced; w may be NULL
 int hb_lr_multidot(hb_lowrank* k, const double* w, const double* x, double sigma_s);
+// device table of row pointers [J rows (m); S rows (l); Y rows (l)] -> k->rowptr_dev, k->rows_aligned
+int hb_lr_refresh_rowptr(hb_lowrank* k);

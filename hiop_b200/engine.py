@@ -264,6 +264,14 @@ class KKTLinSysLowRank:
             self.ctx.sync()
         return ll, sg.value, St, Yt, L[:ll * ll].reshape(ll, ll).copy(), D[:ll].copy()
 
+    def lsq_duals(self, grad_f, zl, zu, vl, vu, yc, yd) -> bool:
+        """hiopDualsLsqUpdate: least-squares yc, yd for the registered Jacobian; False if J J^T + I is not numerically SPD."""
+        rc = self.ctx.L.hb_lowrank_lsq_duals(self.h, _ptr(grad_f), _ptr(zl), _ptr(zu), _ptr(vl), _ptr(vu), _ptr(yc), _ptr(yd))
+        if rc == -4:
+            return False
+        check(rc, "hb_lowrank_lsq_duals")
+        return True
+
     def update(self, zl, sxl, zu, sxu, vl, sdl, vu, sdu) -> bool:
         self._keep["it"] = (zl, sxl, zu, sxu, vl, sdl, vu, sdu)
         check(self.ctx.L.hb_lowrank_update(self.h, *[_ptr(t) for t in (zl, sxl, zu, sxu, vl, sdl, vu, sdu)]), "hb_lowrank_update")

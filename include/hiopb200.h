@@ -189,6 +189,13 @@ int hb_lowrank_secant_reset(hb_lowrank* k, double sigma0, int sigma_strategy);
 int hb_lowrank_secant_update(hb_lowrank* k, const double* x, const double* grad_f, const double* yc, const double* yd,
                              int jacobian_is_constant, int* status);
 int hb_lowrank_secant_state(hb_lowrank* k, int* l, double* sigma, const double** St, const double** Yt, double* L_host, double* D_host);
+/* LSQ multiplier (re)computation hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (src/Optimization/hiopDualsUpdater.cpp:
+ * 232-332, DPOTRF/DPOTRS :690-735): solves [Jc Jc^T, Jc Jd^T; ., Jd Jd^T + I] [yc; yd] = -[Jc vx; Jd vx + (vl - vu)],
+ * vx = grad_f - zl + zu, with the Jacobian registered by hb_lowrank_set_jacobian. J J^T is one pass of the condensation
+ * kernel (mode as hb_lowrank_set_condense_mode) + all-reduce; Cholesky on every rank. HB_ERR_NUMERIC if not SPD (the
+ * reference then keeps the duals of the line search, hiopDualsUpdater.cpp:263-267). */
+int hb_lowrank_lsq_duals(hb_lowrank* k, const double* grad_f, const double* zl, const double* zu, const double* vl, const double* vu,
+                         double* yc, double* yd);
 /* update(): Dx = zl/sxl|ixl + zu/sxu|ixu, DhInv = 1/(sigma+Dx), Dd = vl/sdl|idl + vu/sdu|idu, Dd_inv = 1/Dd in ONE fused
  * pass (hiopKKTLinSys.cpp:1057-1094 + hiopHessianLowRank.cpp:221-233; 7 n-passes in the reference). Borrows the
  * iterate pointers until the next update (they are read again by hb_lowrank_compute_directions). */

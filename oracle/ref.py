@@ -50,6 +50,8 @@ def lib():
         L.ref_qn_set_sigma_strategy.restype = None
         L.ref_densekkt_build.argtypes = [ctypes.c_int] * 4 + [dp] * 15 + [ctypes.POINTER(dp), dp]
         L.ref_densekkt_build.restype = ctypes.c_int
+        L.ref_qn_lsq_duals.argtypes = [ctypes.c_void_p, dp, dp, dp]
+        L.ref_qn_lsq_duals.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -212,6 +214,14 @@ class RefQn:
 
     def set_sigma_strategy(self, strategy: int, sigma0: float = 1.0):
         lib().ref_qn_set_sigma_strategy(self.h, int(strategy), ctypes.c_double(sigma0))
+
+    def lsq_duals(self, grad_f):
+        """hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update -> (yc, yd)."""
+        g = np.ascontiguousarray(grad_f, dtype=np.float64)
+        yc, yd = np.zeros(max(self.meq, 1)), np.zeros(max(self.mineq, 1))
+        rc = lib().ref_qn_lsq_duals(self.h, g.ctypes.data_as(dp), yc.ctypes.data_as(dp), yd.ctypes.data_as(dp))
+        assert rc == 0
+        return yc[:self.meq].copy(), yd[:self.mineq].copy()
 
     def _sizes(self):
         return dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,

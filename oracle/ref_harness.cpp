@@ -28,6 +28,7 @@
 #include "hiopVectorCompoundPD.hpp"
 #include "hiopKrylovSolver.hpp"
 #include "hiopKKTLinSysDense.hpp"
+#include "hiopDualsUpdater.hpp"
 #include "LinAlgFactory.hpp"
 
 #include <chrono>
@@ -297,6 +298,20 @@ void ref_qn_set_sigma_strategy(void* h, int strategy, double sigma0)
   c->hess->sigma_update_strategy = strategy;
   c->hess->sigma0 = sigma0;
   c->hess->sigma = sigma0;
+}
+
+/// hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (hiopDualsUpdater.cpp:232-332, DPOTRF/DPOTRS :690-735): the LSQ
+/// multipliers yc, yd from [Jc Jc^T, Jc Jd^T; ., Jd Jd^T + I] y = -[Jc vx; Jd vx + vd], vx = grad_f - zl + zu, vd = vl - vu.
+/// Uses the Jacobians and zl, zu, vl, vu already planted by ref_qn_set_jac / ref_qn_set_iterate.
+int ref_qn_lsq_duals(void* h, const double* grad_f, double* yc, double* yd)
+{
+  QnCtx* c = (QnCtx*)h;
+  set_vec(c->gradf, grad_f);
+  hiopDualsLsqUpdateLinsysRedDenseSymPD lsq(c->nlp);
+  hiopDualsLsqUpdateLinsysRedDense* base = &lsq;
+  bool ok = base->do_lsq_update(*c->it, *c->gradf, *c->Jc, *c->Jd);
+  get_vec(c->it->yc, yc); get_vec(c->it->yd, yd);
+  return ok ? 0 : -1;
 }
 
 namespace {

@@ -170,6 +170,19 @@ def test_dense_newton_kkt_matrix_matches_reference(form, nx, neq, nineq, dw, dc)
     np.testing.assert_array_equal(M, M_r)          # same additions in the same order: bit-identical, lower triangle zero
 
 
+@pytest.mark.parametrize("n,m", [(800, 14), (300, 1), (500, 40)])
+def test_lsq_duals_match_reference(n, m):
+    """hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (initial / recalculated multipliers)."""
+    p = synth.make_qn_problem(n, m, 0)
+    q = _ref_system(p)
+    g = np.random.default_rng(8).standard_normal(n)
+    yc_r, yd_r = q.lsq_duals(g)
+    yc, yd = ko.lsq_duals(p.Jc, p.Jd, g, p.zl, p.zu, p.vl, p.vu)
+    for a, b in ((yc, yc_r), (yd, yd_r)):
+        assert np.abs(a - b).max(initial=0.0) <= 1e-10 * max(1.0, np.abs(b).max(initial=0.0))
+    q.close()
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
