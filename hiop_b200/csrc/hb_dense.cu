@@ -67,19 +67,23 @@ k_panel(double* __restrict__ A, int lda, int N, int k0, int nb, double* __restri
         double a[16];
 #pragma unroll
         for(int c = 0; c < 16; c++) a[c] = (lane < 16 && c <= lane) ? D[kb + c][kb + lane] : 0.0;
-#pragma unroll
-        for(int j = 0; j < 16; j++) {
-          const double d = __shfl_sync(0xffffffffu, a[j], j);
-          if(!(d > 0.0) && lane == 0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + kb + j + 1);
-          const double l = sqrt(d);
-          if(lane == j) a[j] = l;
-          else if(lane > j) a[j] = a[j] / l;
-#pragma unroll
-          for(int c = j + 1; c < 16; c++) {
-            const double lc = __shfl_sync(0xffffffffu, a[j], c);
-            if(lane >= c) a[c] -= a[j] * lc;
-          }
-        }
+        // spelled out per column: the 16 x 15 nest does not get fully unrolled otherwise and a[] lands in local memory
+#define PANEL_CHOL_COL(j)                                                                      \
+  {                                                                                            \
+    const double d = __shfl_sync(0xffffffffu, a[j], j);                                        \
+    if(!(d > 0.0) && lane == 0 && blockIdx.x == 0) atomicCAS(info, 0, k0 + kb + j + 1);       \
+    const double l = sqrt(d);                                                                  \
+    if(lane == j) a[j] = l;                                                                    \
+    else if(lane > j) a[j] = a[j] / l;                                                         \
+    _Pragma("unroll") for(int c = j + 1; c < 16; c++) {                                        \
+      const double lc = __shfl_sync(0xffffffffu, a[j], c);                                     \
+      if(lane >= c) a[c] -= a[j] * lc;                                                         \
+    }                                                                                          \
+  }
+        PANEL_CHOL_COL(0) PANEL_CHOL_COL(1) PANEL_CHOL_COL(2) PANEL_CHOL_COL(3) PANEL_CHOL_COL(4) PANEL_CHOL_COL(5) PANEL_CHOL_COL(6)
+        PANEL_CHOL_COL(7) PANEL_CHOL_COL(8) PANEL_CHOL_COL(9) PANEL_CHOL_COL(10) PANEL_CHOL_COL(11) PANEL_CHOL_COL(12) PANEL_CHOL_COL(13)
+        PANEL_CHOL_COL(14) PANEL_CHOL_COL(15)
+#undef PANEL_CHOL_COL
 #pragma unroll
         for(int c = 0; c < 16; c++)
           if(lane < 16 && c <= lane) D[kb + c][kb + lane] = a[c];
@@ -741,8 +745,15 @@ k_chol_solve(const double* __restrict__ F, int ldf, int N, double* __restrict__ 
 constexpr size_t TRAILING_SMEM = sizeof(double) * 2 * NB * TLD;
 static bool g_trailing_attr = false;
 
+int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, bool* used);
+
 int hb_dense_factor_blocked(hb_ctx* c, int N, double* A, int lda, bool ldl, double* Wpanel /* NB*N doubles if ldl */, int* info_dev)
 {
+  if(!ldl) { // small SPD systems: one cooperative launch instead of two launches per panel (hb_chol_coop.cu)
+    bool used = false;
+    HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, &used));
+    if(used) return HB_OK;
+  }
   if(!g_trailing_attr) {
     HB_CUDA(cudaFuncSetAttribute(k_trailing, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TRAILING_SMEM));
     g_trailing_attr = true;
