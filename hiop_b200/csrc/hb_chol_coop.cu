@@ -146,7 +146,8 @@ __device__ void factor_diag(CoopSmem& S, int k0, int* info, bool report, long lo
 }
 
 __global__ void __launch_bounds__(CT, 1)
-k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, long long* __restrict__ prof /* may be NULL: 10 cycle counters of CTA 0 */)
+k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, double* __restrict__ invd /* may be NULL: 16 x 16 inverses per panel */,
+            long long* __restrict__ prof /* may be NULL: 10 cycle counters of CTA 0 */)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   CoopSmem& S = *reinterpret_cast<CoopSmem*>(smem_raw);
@@ -179,6 +180,8 @@ k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, long
         const int j = e / nb, i = e % nb;
         if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DS + i];
       }
+      if(invd)
+        for(int e = tid; e < 4 * 16 * 17; e += CT) invd[(size_t)(k0 / CB) * (4 * 16 * 17) + e] = S.Inv[e];
     }
     const int r0 = k0 + nb;
     const int R = N - r0;
@@ -310,13 +313,181 @@ k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, long
 #undef PROF
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cooperative SPD solve with the factor above: x = S F^-T F^-1 S rhs, then the residual check against the unscaled matrix and
+// up to max_refine corrections (hiopKKTLinSysLowRank::solveWithRefin, hiopKKTLinSys.cpp:1192-1350: ||rhs - N x||_inf < tol).
+// The one-CTA version streamed the 8 MB factor twice + N once through a single SM (0.74 ms at N = 1000). Here every CTA solves
+// the 64-entry diagonal block redundantly from the stored 16 x 16 inverses and updates only its own slice of the remaining
+// vector (rows in the forward sweep, columns in the backward sweep); one grid barrier per block.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SolveSmem
+{
+  double z[CB];
+  double y[16];
+  double Inv[4 * 16 * 17];
+  double L[CB * DS]; // L[j*DS + i] = element (i, j) of the diagonal block of the factor
+  double red[32];
+};
+
+// in-block solve with the lower triangle (trans = false: L z' = z; true: L^T z' = z), result in S.z
+__device__ void block_solve(SolveSmem& S, bool trans)
+{
+  const int tid = threadIdx.x;
+  for(int step = 0; step < 4; step++) {
+    const int sb = trans ? 3 - step : step;
+    const double* inv = S.Inv + sb * 16 * 17;
+    if(tid < 16) {
+      double acc = 0.0;
+#pragma unroll
+      for(int q = 0; q < 16; q++) {
+        // (T^-1 z)_c = sum_{q<=c} inv[c][q] z[q];   (T^-T z)_c = sum_{q>=c} inv[q][c] z[q]
+        const double w = trans ? (q >= tid ? inv[q * 17 + tid] : 0.0) : (q <= tid ? inv[tid * 17 + q] : 0.0);
+        acc += w * S.z[sb * 16 + q];
+      }
+      S.y[tid] = acc;
+    }
+    __syncthreads();
+    if(tid < 16) S.z[sb * 16 + tid] = S.y[tid];
+    // eliminate the solved 16 unknowns from the rest of the block
+    if(!trans) {
+      const int r = (sb + 1) * 16 + tid - 16; // rows below: tid 16.. -> r = (sb+1)*16 ..
+      if(tid >= 16 && r < CB) {
+        double acc = 0.0;
+#pragma unroll
+        for(int q = 0; q < 16; q++) acc += S.L[(sb * 16 + q) * DS + r] * S.y[q];
+        S.z[r] -= acc;
+      }
+    } else {
+      const int cidx = tid - 16; // columns before: c < sb*16
+      if(tid >= 16 && cidx < sb * 16) {
+        double acc = 0.0;
+#pragma unroll
+        for(int q = 0; q < 16; q++) acc += S.L[cidx * DS + sb * 16 + q] * S.y[q];
+        S.z[cidx] -= acc;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__device__ void load_block(SolveSmem& S, const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd, const double* __restrict__ v, int k0)
+{
+  const int tid = threadIdx.x;
+  const int nb = min(CB, N - k0);
+  for(int e = tid; e < 4 * 16 * 17; e += CT) S.Inv[e] = invd[(size_t)(k0 / CB) * (4 * 16 * 17) + e];
+  for(int e = tid; e < CB * CB; e += CT) {
+    const int j = e / CB, i = e % CB;
+    S.L[j * DS + i] = (i < nb && j < nb && i >= j) ? LC(F, ldf, k0 + i, k0 + j) : 0.0;
+  }
+  if(tid < CB) S.z[tid] = tid < nb ? v[k0 + tid] : 0.0;
+  __syncthreads();
+}
+
+// v <- F^-T F^-1 v (v in global memory, length N)
+__device__ void coop_potrs(SolveSmem& S, cg::grid_group& grid, const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd,
+                           double* __restrict__ v)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
+  const int nblk = (N + CB - 1) / CB;
+  for(int kb = 0; kb < nblk; kb++) { // forward: L z = v
+    const int k0 = kb * CB, nb = min(CB, N - k0);
+    load_block(S, F, ldf, N, invd, v, k0);
+    block_solve(S, false);
+    const int r0 = k0 + nb, R = N - r0;
+    if(R > 0) {
+      const int per = (R + G - 1) / G;
+      const int first = r0 + b * per, last = min(N, first + per);
+      for(int r = first + warp; r < last; r += CT / 32) { // one warp per row: v[r] -= L[r, k0:k0+nb] . z
+        double acc = 0.0;
+        for(int q = lane; q < nb; q += 32) acc += LC(F, ldf, r, k0 + q) * S.z[q];
+        acc = hb_warp_sum(acc);
+        if(lane == 0) v[r] -= acc;
+      }
+    }
+    if(b == 0 && tid < nb) v[k0 + tid] = S.z[tid];
+    grid.sync();
+  }
+  for(int kb = nblk - 1; kb >= 0; kb--) { // backward: L^T x = z
+    const int k0 = kb * CB, nb = min(CB, N - k0);
+    load_block(S, F, ldf, N, invd, v, k0);
+    block_solve(S, true);
+    if(k0 > 0) {
+      const int per = (k0 + G - 1) / G;
+      const int first = b * per, last = min(k0, first + per);
+      for(int cix = first + warp; cix < last; cix += CT / 32) { // one warp per column: v[c] -= L[k0:k0+nb, c] . x_k (contiguous)
+        double acc = 0.0;
+        for(int q = lane; q < nb; q += 32) acc += LC(F, ldf, k0 + q, cix) * S.z[q];
+        acc = hb_warp_sum(acc);
+        if(lane == 0) v[cix] -= acc;
+      }
+    }
+    if(b == 0 && tid < nb) v[k0 + tid] = S.z[tid];
+    grid.sync();
+  }
+}
+
+__global__ void __launch_bounds__(CT, 1)
+k_spd_solve_coop(const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd, const double* __restrict__ s,
+                 const double* __restrict__ Nref, int ldn, const double* __restrict__ rhs, double* __restrict__ x, double* __restrict__ work /* 2N+2 */,
+                 double tol, int max_refine, double* __restrict__ stats)
+{
+  __shared__ SolveSmem S;
+  cg::grid_group grid = cg::this_grid();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
+  const int gtid = b * CT + tid, gthreads = G * CT;
+  double* v = work;     // vector being solved (scaled)
+  double* r = work + N; // residual
+  unsigned long long* nrm_bits = reinterpret_cast<unsigned long long*>(work + 2 * N); // two slots, used alternately
+  for(int i = gtid; i < N; i += gthreads) v[i] = rhs[i] * s[i];
+  if(gtid < 2) nrm_bits[gtid] = 0ull;
+  grid.sync();
+  coop_potrs(S, grid, F, ldf, N, invd, v);
+  for(int i = gtid; i < N; i += gthreads) x[i] = v[i] * s[i];
+  grid.sync();
+  int nref = 0;
+  double nrm = 0.0;
+  while(true) {
+    // r = rhs - Nref x, one warp per row; ||r||_inf through an integer max on the bit pattern (r >= 0)
+    unsigned long long* slot = nrm_bits + (nref & 1);
+    double wmax = 0.0;
+    for(int i = b * (CT / 32) + warp; i < N; i += G * (CT / 32)) {
+      double acc = 0.0;
+      const double* row = Nref + (size_t)i * ldn;
+      for(int j = lane; j < N; j += 32) acc += row[j] * x[j];
+      acc = hb_warp_sum(acc);
+      const double ri = rhs[i] - acc;
+      if(lane == 0) r[i] = ri;
+      wmax = fmax(wmax, fabs(ri));
+    }
+    if(lane == 0) {
+      const double m = wmax == wmax ? wmax : __longlong_as_double(0x7ff0000000000000LL); // NaN -> +inf so that it wins the max
+      atomicMax(slot, (unsigned long long)__double_as_longlong(m));
+    }
+    grid.sync();
+    nrm = __longlong_as_double((long long)*slot);
+    if(!(nrm >= tol) || nrm > 1.7e308 || nref >= max_refine) break;
+    if(gtid == 0) nrm_bits[(nref + 1) & 1] = 0ull; // the other slot is idle until the next round's barrier
+    for(int i = gtid; i < N; i += gthreads) v[i] = r[i] * s[i];
+    grid.sync();
+    coop_potrs(S, grid, F, ldf, N, invd, v);
+    for(int i = gtid; i < N; i += gthreads) x[i] += v[i] * s[i];
+    grid.sync();
+    nref++;
+  }
+  if(gtid == 0) {
+    stats[0] = (double)nref;
+    stats[1] = nrm > 1.7e308 ? __longlong_as_double(0x7ff8000000000000LL) : nrm;
+  }
+}
+
 bool g_coop_checked = false, g_coop_ok = false;
 int g_coop_max_ctas = 0;
 
 } // namespace
 
 // returns HB_OK and sets *used = true when the cooperative kernel ran; *used = false -> caller uses the multi-launch path
-int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, bool* used)
+int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* used)
 {
   *used = false;
   if(N <= CB || N > 2048) return HB_OK;
@@ -344,8 +515,34 @@ int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, bool
   if(G < 1) G = 1;
   HB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), c->stream));
   long long* prof = nullptr;
-  void* args[] = {&A, &lda, &N, &info_dev, &prof};
+  void* args[] = {&A, &lda, &N, &info_dev, &invd, &prof};
   HB_CUDA(cudaLaunchCooperativeKernel((const void*)k_chol_coop, dim3(G), dim3(CT), args, sizeof(CoopSmem), c->stream));
+  HB_LAUNCHED();
+  *used = true;
+  return HB_OK;
+}
+
+// cooperative solve + refinement; invd must come from hb_dense_chol_coop of the same factor. work: 2N+2 doubles.
+int hb_dense_spd_solve_coop(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
+                            const double* rhs, double* x, double* work, double tol, int max_refine, double* stats_dev, bool* used)
+{
+  *used = false;
+  if(!g_coop_ok || !invd || N <= CB || N > 2048) return HB_OK;
+  static bool attr = false;
+  static int max_ctas = 0;
+  if(!attr) {
+    int occ = 0;
+    if(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spd_solve_coop, CT, 0) != cudaSuccess || occ < 1) {
+      cudaGetLastError();
+      return HB_OK;
+    }
+    max_ctas = c->num_sms;
+    attr = true;
+  }
+  int G = (N + 7) / 8; // ~8 rows / columns per CTA in the widest sweep step, one row of the residual per warp
+  if(G > max_ctas) G = max_ctas;
+  void* args[] = {&F, &ldf, &N, &invd, &s, &Nref, &ldn, &rhs, &x, &work, &tol, &max_refine, &stats_dev};
+  HB_CUDA(cudaLaunchCooperativeKernel((const void*)k_spd_solve_coop, dim3(G), dim3(CT), args, 0, c->stream));
   HB_LAUNCHED();
   *used = true;
   return HB_OK;

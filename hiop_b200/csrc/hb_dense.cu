@@ -745,13 +745,15 @@ k_chol_solve(const double* __restrict__ F, int ldf, int N, double* __restrict__ 
 constexpr size_t TRAILING_SMEM = sizeof(double) * 2 * NB * TLD;
 static bool g_trailing_attr = false;
 
-int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, bool* used);
+int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* used);
+int hb_dense_spd_solve_coop(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
+                            const double* rhs, double* x, double* work, double tol, int max_refine, double* stats_dev, bool* used);
 
 int hb_dense_factor_blocked(hb_ctx* c, int N, double* A, int lda, bool ldl, double* Wpanel /* NB*N doubles if ldl */, int* info_dev)
 {
   if(!ldl) { // small SPD systems: one cooperative launch instead of two launches per panel (hb_chol_coop.cu)
     bool used = false;
-    HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, &used));
+    HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, nullptr, &used));
     if(used) return HB_OK;
   }
   if(!g_trailing_attr) {
@@ -827,6 +829,28 @@ int hb_dense_equilibrate(hb_ctx* c, int N, const double* Nfull, int ldn, double*
   k_equilibrate<<<g, 256, 0, c->stream>>>(Nfull, ldn, N, F, ldf, s);
   HB_LAUNCHED();
   return HB_OK;
+}
+
+// SPD factorization that also keeps the 16 x 16 diagonal inverses for the cooperative solve (invd: HB_CHOL_INV_DOUBLES(N) doubles);
+// *have_inv tells whether they were produced (small / large N use the multi-launch path and the one-CTA solve)
+int hb_dense_chol_with_inverses(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* have_inv)
+{
+  *have_inv = false;
+  HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, invd, have_inv));
+  if(*have_inv) return HB_OK;
+  return hb_dense_factor_blocked(c, N, A, lda, false, nullptr, info_dev);
+}
+
+int hb_dense_spd_solve_refine2(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
+                               const double* rhs, double* x, double* work2N2, double tol, int max_refine, double* stats_dev)
+{
+  if(N == 0) return HB_OK;
+  if(invd) {
+    bool used = false;
+    HB_CHECK(hb_dense_spd_solve_coop(c, N, F, ldf, invd, s, Nref, ldn, rhs, x, work2N2, tol, max_refine, stats_dev, &used));
+    if(used) return HB_OK;
+  }
+  return hb_dense_spd_solve_refine(c, N, F, ldf, s, Nref, ldn, rhs, x, work2N2, tol, max_refine, stats_dev);
 }
 
 int hb_dense_spd_solve_refine(hb_ctx* c, int N, const double* F, int ldf, const double* s, const double* Nref, int ldn, const double* rhs,

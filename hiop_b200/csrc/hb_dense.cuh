@@ -15,3 +15,10 @@ int hb_dense_tri_solve(hb_ctx* c, int N, const double* F, int ldf, bool ldl, dou
 int hb_dense_equilibrate(hb_ctx* c, int N, const double* Nfull, int ldn, double* F, int ldf, double* s);
 int hb_dense_spd_solve_refine(hb_ctx* c, int N, const double* F, int ldf, const double* s, const double* Nref, int ldn, const double* rhs,
                               double* x, double* work2N, double tol, int max_refine, double* stats_dev);
+
+// Cholesky that keeps the 16 x 16 diagonal inverses when the cooperative kernel runs (64 < N <= 2048), and the matching solve.
+#define HB_CHOL_INV_DOUBLES(N) ((size_t)(((N) + 63) / 64) * (4 * 16 * 17))
+int hb_dense_chol_with_inverses(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* have_inv);
+int hb_dense_spd_solve_refine2(hb_ctx* c, int N, const double* F, int ldf, const double* invd /* NULL: one-CTA solve */, const double* s,
+                               const double* Nref, int ldn, const double* rhs, double* x, double* work2N2, double tol, int max_refine,
+                               double* stats_dev);

@@ -445,7 +445,7 @@ int do_condense(hb_lowrank* k)
         m, k->meq, l, k->Caug, Ma, k->U, k->Z, k->Dd_inv, k->Nmat);
     HB_LAUNCHED();
     HB_CHECK(hb_dense_equilibrate(c, m, k->Nmat, m, k->F, m, k->svec));
-    HB_CHECK(hb_dense_factor_blocked(c, m, k->F, m, false, nullptr, k->info + 1));
+    HB_CHECK(hb_dense_chol_with_inverses(c, m, k->F, m, k->info + 1, k->Finv, &k->have_finv));
   }
   HB_CUDA(cudaMemcpyAsync(k->info_host, k->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
@@ -489,7 +489,8 @@ extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_i
   HB_CHECK(dmalloc(&k->V, (size_t)l2 * l2)); HB_CHECK(dmalloc(&k->Mdir, (size_t)l2 * l2));
   HB_CHECK(dmalloc(&k->U, (size_t)m * l2)); HB_CHECK(dmalloc(&k->Z, (size_t)m * l2));
   HB_CHECK(dmalloc(&k->Nmat, (size_t)m * m)); HB_CHECK(dmalloc(&k->F, (size_t)m * m));
-  HB_CHECK(dmalloc(&k->svec, m)); HB_CHECK(dmalloc(&k->rhs, m)); HB_CHECK(dmalloc(&k->dy, m)); HB_CHECK(dmalloc(&k->work, 2 * (size_t)m));
+  HB_CHECK(dmalloc(&k->svec, m)); HB_CHECK(dmalloc(&k->rhs, m)); HB_CHECK(dmalloc(&k->dy, m)); HB_CHECK(dmalloc(&k->work, 2 * (size_t)m + 2));
+  HB_CHECK(dmalloc(&k->Finv, HB_CHOL_INV_DOUBLES(m > 0 ? m : 1)));
   HB_CHECK(dmalloc(&k->stats, 4));
   HB_CHECK(dmalloc(&k->nv1, n_local)); HB_CHECK(dmalloc(&k->nv2, n_local));
   HB_CHECK(dmalloc(&k->p2l, l2));
@@ -512,7 +513,7 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);
@@ -640,7 +641,8 @@ extern "C" int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const doub
     k_sub_stacked<<<(m + 127) / 128, 128, 0, c->stream>>>(k->meq, k->mineq, k->rhs, ryc, ryd);
     HB_LAUNCHED();
     // 3. N dy = rhs with residual-driven refinement               :1169, 1192-1350
-    HB_CHECK(hb_dense_spd_solve_refine(c, m, k->F, m, k->svec, k->Nmat, m, k->rhs, k->dy, k->work, 1e-8, 3, k->stats));
+    HB_CHECK(hb_dense_spd_solve_refine2(c, m, k->F, m, k->have_finv ? k->Finv : nullptr, k->svec, k->Nmat, m, k->rhs, k->dy, k->work, 1e-8, 3,
+                                        k->stats));
     if(k->meq) HB_CUDA(cudaMemcpyAsync(dyc, k->dy, sizeof(double) * k->meq, cudaMemcpyDeviceToDevice, c->stream));
     if(k->mineq) HB_CUDA(cudaMemcpyAsync(dyd, k->dy + k->meq, sizeof(double) * k->mineq, cudaMemcpyDeviceToDevice, c->stream));
     // 4. rx = rx - J^T dy                                          :1178

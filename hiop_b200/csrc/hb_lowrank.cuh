@@ -41,6 +41,8 @@ struct hb_lowrank
   // secant memory owned by the engine (hb_secant.cu): S_t, Y_t (lmax x n), previous iterate / gradient / Jacobian
   double *sec_S = nullptr, *sec_Y = nullptr, *sec_xprev = nullptr, *sec_gprev = nullptr, *sec_Jprev = nullptr;
   double sec_L[64 * 64] = {0}, sec_D[64] = {0}; // host copies of L (row-major, stride l) and D; lmax <= 64 in this mode
+  double* Finv = nullptr;  // 16 x 16 inverses of the diagonal of F (cooperative Cholesky / solve)
+  bool have_finv = false;
   double* lsq_M = nullptr; // m x m LSQ matrix / Cholesky factor + 2 m-vectors (hb_lsq.cu)
   int sec_lcurr = -1, sec_strategy = 1;
   double sec_sigma0 = 1.0;

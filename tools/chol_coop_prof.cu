@@ -17,7 +17,8 @@ int main(int argc, char** argv)
   for(int G : {148, 120}) {
     cudaMemcpy(A, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice);
     cudaMemset(prof, 0, 80); cudaMemset(info, 0, 4);
-    void* args[] = {&A, &lda, &n, &info, &prof};
+    double* invd = nullptr;
+    void* args[] = {&A, &lda, &n, &info, &invd, &prof};
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0);
     cudaError_t rc = cudaLaunchCooperativeKernel((const void*)k_chol_coop, dim3(G), dim3(CT), args, sizeof(CoopSmem), 0);
