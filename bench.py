@@ -409,7 +409,8 @@ def run_engine(args):
             h2d = 8 * (m * n_local + 5 * n_local + 4 * m_ineq + m)
             d2h = 8 * (n_local + m)
             e2e = {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms,
-                   "steps": e2e_steps, "note": "hb_lowrank_kkt_system_host: J (8 GB) + iterate + rhs copied from pinned host memory every step"}
+                   "steps": e2e_steps, "note": "hb_lowrank_kkt_system_host: J (8 GB) + iterate + rhs copied from pinned host memory every step; J travels in 16 column "
+                           "chunks on a copy stream while the FP64-DMMA kernel condenses the chunks already on the device (exact FP64 path)"}
 
     if rank != 0:
         if world > 1:

@@ -141,14 +141,18 @@ k_multidot_partial(long long n, int l, const double* __restrict__ S, const doubl
     if(threadIdx.x == 0 && q0 + c < n2) partial[(size_t)blockIdx.x * n2 + q0 + c] = r;
   }
 }
-__global__ void k_multidot_final(int np, int l, double sigma_s, const double* __restrict__ partial, double* __restrict__ out)
+// one CTA per output: 128 threads stride over the per-CTA partials, fixed-order block reduction (a single thread walking
+// all ~1200 partials took 98 us)
+__global__ void __launch_bounds__(128)
+k_multidot_final(int np, int l, double sigma_s, const double* __restrict__ partial, double* __restrict__ out)
 {
+  __shared__ double sm[4];
   const int n2 = 2 * l;
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if(q >= n2) return;
+  const int q = blockIdx.x;
   double s = 0.0;
-  for(int p = 0; p < np; p++) s += partial[(size_t)p * n2 + q];
-  out[q] = q < l ? s * sigma_s : s;
+  for(int p = threadIdx.x; p < np; p += 128) s += partial[(size_t)p * n2 + q];
+  s = hb_block_sum<128>(s, sm);
+  if(threadIdx.x == 0) out[q] = q < l ? s * sigma_s : s;
 }
 // x[k] = w[k] * (r[k] - sigma*sum_q S_q[k] p_q - sum_q Y_q[k] p_{l+q})   (hiopHessianLowRank::solve steps 4-5, :526-535)
 // general form: out = beta*out + alpha*( base[k]*r[k] ... ) handled by flags below
@@ -211,15 +215,26 @@ k_gemv_rows_partial(int m, long long n, const double* __restrict__ A, long long 
     if(lane == 0) partial[(size_t)blockIdx.x * m + i] = acc;
   }
 }
-// y[i] = beta*y[i] + alpha*sum_chunks partial[c][i]
-__global__ void k_gemv_rows_final(int m, int nchunks, const double* __restrict__ partial, double beta, double* __restrict__ y, double alpha)
+// y[i] = beta*y[i] + alpha*sum_chunks partial[c][i]: 32 rows x 8 chunk-classes per CTA (coalesced along i), fixed-order combine
+__global__ void __launch_bounds__(256)
+k_gemv_rows_final(int m, int nchunks, const double* __restrict__ partial, double beta, double* __restrict__ y, double alpha)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if(i >= m) return;
+  __shared__ double sm[8][33];
+  const int ri = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ri;
   double s = 0.0;
-  for(int c = 0; c < nchunks; c++) s += partial[(size_t)c * m + i];
-  y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + alpha * s;
+  if(i < m)
+    for(int c = part; c < nchunks; c += 8) s += partial[(size_t)c * m + i];
+  sm[part][ri] = s;
+  __syncthreads();
+  if(part == 0 && i < m) {
+    double t = 0.0;
+#pragma unroll
+    for(int p = 0; p < 8; p++) t += sm[p][ri];
+    y[i] = (beta == 0.0 ? 0.0 : beta * y[i]) + alpha * t;
+  }
 }
+
 // y[k] = beta*y[k] + alpha*sum_i A[i][k]*x[i]; each thread owns two adjacent columns
 constexpr int GC_ROWS = 1024; // rows of x staged per pass
 __global__ void __launch_bounds__(ET)
@@ -360,7 +375,7 @@ int multidot(hb_lowrank* k, const double* w, const double* x, double sigma_s)
     k_multidot_partial<<<g, ET, 0, c->stream>>>(k->n, k->l, k->St, k->Yt, k->n, w, x, q0, k->md_partial);
     HB_LAUNCHED();
   }
-  k_multidot_final<<<(n2 + 63) / 64, 64, 0, c->stream>>>(g, k->l, sigma_s, k->md_partial, k->p2l);
+  k_multidot_final<<<n2, 128, 0, c->stream>>>(g, k->l, sigma_s, k->md_partial, k->p2l);
   HB_LAUNCHED();
   HB_CHECK(hb_allreduce_sum(c, k->p2l, n2));
   return HB_OK;
@@ -378,11 +393,11 @@ int gemv_rows(hb_lowrank* k, const double* A, int m, double beta, double* y, dou
   }
   if(c->nranks > 1) {
     // beta*y only on rank 0 before the reduction (hiopMatrixDenseRowMajor.cpp:464-467)
-    k_gemv_rows_final<<<(m + 127) / 128, 128, 0, c->stream>>>(m, nchunks, (const double*)c->ws, c->rank == 0 ? beta : 0.0, y, alpha);
+    k_gemv_rows_final<<<(m + 31) / 32, 256, 0, c->stream>>>(m, nchunks, (const double*)c->ws, c->rank == 0 ? beta : 0.0, y, alpha);
     HB_LAUNCHED();
     HB_CHECK(hb_allreduce_sum(c, y, m));
   } else {
-    k_gemv_rows_final<<<(m + 127) / 128, 128, 0, c->stream>>>(m, nchunks, (const double*)c->ws, beta, y, alpha);
+    k_gemv_rows_final<<<(m + 31) / 32, 256, 0, c->stream>>>(m, nchunks, (const double*)c->ws, beta, y, alpha);
     HB_LAUNCHED();
   }
   return HB_OK;
@@ -413,6 +428,8 @@ int hess_solve(hb_lowrank* k, const double* rhs, double* x)
   return HB_OK;
 }
 
+int condense_finish(hb_lowrank* k);
+
 int do_condense(hb_lowrank* k)
 {
   hb_ctx* c = k->ctx;
@@ -420,15 +437,23 @@ int do_condense(hb_lowrank* k)
   HB_REQUIRE(k->J || k->m == 0, "hb_lowrank_condense: Jacobian not set");
   const int m = k->m, l = k->l, Ma = m + 2 * l;
   HB_CHECK(refresh_rowptr(k));
-  HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
   if(Ma > 0) {
     int mode = k->condense_mode;
     if(mode < 0) mode = (k->n >= 32768 && Ma >= 64) ? 8 : 0; // small systems: slicing + TMA setup do not pay off
     k->condense_used = mode;
     if(mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
     else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, mode));
-    HB_CHECK(hb_allreduce_sum(c, k->Caug, (long long)Ma * Ma));
   }
+  return condense_finish(k);
+}
+
+// everything after C_aug = [J;S;Y] DhInv [J;S;Y]^T (local columns) is in k->Caug
+int condense_finish(hb_lowrank* k)
+{
+  hb_ctx* c = k->ctx;
+  const int m = k->m, l = k->l, Ma = m + 2 * l;
+  HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
+  if(Ma > 0) HB_CHECK(hb_allreduce_sum(c, k->Caug, (long long)Ma * Ma));
   if(l > 0) {
     k_build_V<<<(4 * l * l + 127) / 128, 128, 0, c->stream>>>(m, l, k->sigma, k->Caug, Ma, k->SSt, k->Ld, k->Dd_sec, k->V);
     HB_LAUNCHED();
@@ -513,11 +538,16 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv, k->Ctmp};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);
   cudaFreeHost(k->rowptr_host); cudaFreeHost(k->info_host); cudaFreeHost(k->stats_host);
+  if(k->copy_stream) {
+    cudaStreamDestroy(k->copy_stream);
+    for(cudaEvent_t e : k->chunk_ev) if(e) cudaEventDestroy(e);
+    cudaFree(k->chunk_rowptr_dev); cudaFreeHost(k->chunk_rowptr_host);
+  }
   delete k;
   return HB_OK;
 }
@@ -747,20 +777,77 @@ extern "C" int hb_lowrank_kkt_system_host(hb_lowrank* k, const double* Jc_host, 
                          (size_t)n, (size_t)meq, (size_t)mi};
   for(int i = 0; i < 14; i++)
     if(!k->hbuf[i]) HB_CHECK(dmalloc(&k->hbuf[i], sz[i]));
-  if(Jc_host || Jd_host) {
-    if(!k->hJ) HB_CHECK(dmalloc(&k->hJ, (size_t)k->m * n));
-    if(meq) HB_CUDA(cudaMemcpyAsync(k->hJ, Jc_host, sizeof(double) * (size_t)meq * n, cudaMemcpyHostToDevice, c->stream));
-    if(mi) HB_CUDA(cudaMemcpyAsync(k->hJ + (size_t)meq * n, Jd_host, sizeof(double) * (size_t)mi * n, cudaMemcpyHostToDevice, c->stream));
-    HB_CHECK(hb_lowrank_set_jacobian(k, k->hJ, k->hJ + (size_t)meq * n));
-  }
   const double* src[11] = {zl, sxl, zu, sxu, vl, sdl, vu, sdu, rx, ryc, ryd};
   for(int i = 0; i < 11; i++)
     if(sz[i]) {
       HB_REQUIRE(src[i], "hb_lowrank_kkt_system_host: null host input");
       HB_CUDA(cudaMemcpyAsync(k->hbuf[i], src[i], sizeof(double) * sz[i], cudaMemcpyHostToDevice, c->stream));
     }
+  const int m = k->m, Ma = m + 2 * k->l;
+  const bool have_J = Jc_host || Jd_host;
+  // The 8 m n bytes of J dominate this call (PCIe). When they are large, J is uploaded in column chunks on a second stream and
+  // each chunk is condensed (exact FP64 DMMA kernel, which needs no global row scaling) while the next one is in flight; the
+  // partial C_aug are added in chunk order, so the result does not depend on timing.
+  static const size_t chunk_min_bytes = getenv("HB_HOST_CHUNK_MIN_BYTES") ? (size_t)atoll(getenv("HB_HOST_CHUNK_MIN_BYTES")) : ((size_t)256 << 20);
+  const bool chunked = have_J && Ma > 0 && (k->condense_mode <= 0) && (size_t)m * n * sizeof(double) >= chunk_min_bytes && n >= 2048;
+  if(have_J && !k->hJ) HB_CHECK(dmalloc(&k->hJ, (size_t)k->m * n));
+  if(have_J && !chunked) {
+    if(meq) HB_CUDA(cudaMemcpyAsync(k->hJ, Jc_host, sizeof(double) * (size_t)meq * n, cudaMemcpyHostToDevice, c->stream));
+    if(mi) HB_CUDA(cudaMemcpyAsync(k->hJ + (size_t)meq * n, Jd_host, sizeof(double) * (size_t)mi * n, cudaMemcpyHostToDevice, c->stream));
+  }
+  if(have_J) HB_CHECK(hb_lowrank_set_jacobian(k, k->hJ, k->hJ + (size_t)meq * n));
   HB_CHECK(hb_lowrank_update(k, k->hbuf[0], k->hbuf[1], k->hbuf[2], k->hbuf[3], k->hbuf[4], k->hbuf[5], k->hbuf[6], k->hbuf[7]));
-  HB_CHECK(do_condense(k));
+  if(!chunked) {
+    HB_CHECK(do_condense(k));
+  } else {
+    constexpr int NCH = 16;
+    if(!k->copy_stream) {
+      HB_CUDA(cudaStreamCreateWithFlags(&k->copy_stream, cudaStreamNonBlocking));
+      for(int q = 0; q < 32; q++) HB_CUDA(cudaEventCreateWithFlags(&k->chunk_ev[q], cudaEventDisableTiming));
+      HB_CUDA(cudaMalloc(&k->chunk_rowptr_dev, sizeof(double*) * 32 * (size_t)(k->m + 2 * k->lmax)));
+      HB_CUDA(cudaMallocHost(&k->chunk_rowptr_host, sizeof(double*) * 32 * (size_t)(k->m + 2 * k->lmax)));
+    }
+    if(!k->Ctmp) HB_CHECK(dmalloc(&k->Ctmp, (size_t)(k->m + 2 * k->lmax) * (k->m + 2 * k->lmax)));
+    HB_CHECK(refresh_rowptr(k)); // k->rowptr_host: full-length rows of [J; S; Y]
+    long long csz = ((n + NCH - 1) / NCH + 63) & ~63LL;
+    int nch = (int)((n + csz - 1) / csz);
+    for(int q = 0; q < nch; q++)
+      for(int i = 0; i < Ma; i++) k->chunk_rowptr_host[(size_t)q * Ma + i] = k->rowptr_host[i] + q * csz;
+    HB_CUDA(cudaMemcpyAsync(k->chunk_rowptr_dev, k->chunk_rowptr_host, sizeof(double*) * (size_t)nch * Ma, cudaMemcpyHostToDevice, c->stream));
+    // the copy stream starts after the (small) uploads above were enqueued; it only ever writes k->hJ
+    HB_CUDA(cudaEventRecord(k->chunk_ev[31], c->stream));
+    HB_CUDA(cudaStreamWaitEvent(k->copy_stream, k->chunk_ev[31], 0));
+    // Copies are submitted only LOOKAHEAD chunks ahead of the kernels that consume them: if the two streams ever share a hardware
+    // work queue (CUDA_DEVICE_MAX_CONNECTIONS) commands run in submission order, and "all copies, then all kernels" would serialise.
+    constexpr int LOOKAHEAD = 3;
+    auto submit_copy = [&](int q) -> int {
+      const long long c0 = q * csz, w = (c0 + csz <= n ? csz : n - c0);
+      if(meq)
+        HB_CUDA(cudaMemcpy2DAsync(k->hJ + c0, sizeof(double) * n, Jc_host + c0, sizeof(double) * n, sizeof(double) * w, meq, cudaMemcpyHostToDevice,
+                                  k->copy_stream));
+      if(mi)
+        HB_CUDA(cudaMemcpy2DAsync(k->hJ + (size_t)meq * n + c0, sizeof(double) * n, Jd_host + c0, sizeof(double) * n, sizeof(double) * w, mi,
+                                  cudaMemcpyHostToDevice, k->copy_stream));
+      HB_CUDA(cudaEventRecord(k->chunk_ev[q], k->copy_stream));
+      return HB_OK;
+    };
+    for(int q = 0; q < nch && q < LOOKAHEAD; q++) HB_CHECK(submit_copy(q));
+    k->condense_used = 0;
+    // timing-enabled cudaEventRecord between the kernels serialises the compute stream against the copy engine (measured: with
+    // hb_ctx_enable_timing the first kernel started when the last copy ended, 183 ms instead of 151 ms per call) -> off in here
+    const bool timing_saved = c->timing;
+    c->timing = false;
+    for(int q = 0; q < nch; q++) {
+      const long long c0 = q * csz, w = (c0 + csz <= n ? csz : n - c0);
+      HB_CUDA(cudaStreamWaitEvent(c->stream, k->chunk_ev[q], 0));
+      // csz is a multiple of 64 columns: every chunk keeps the 16-byte alignment of its rows
+      HB_CHECK(hb_syrk_rows(c, Ma, w, k->chunk_rowptr_dev + (size_t)q * Ma, k->rows_aligned, k->DhInv + c0, q == 0 ? k->Caug : k->Ctmp, Ma));
+      if(q > 0) HB_CHECK(hb_vec_axpy(c, (long long)Ma * Ma, k->Caug, 1.0, k->Ctmp));
+      if(q + LOOKAHEAD < nch) HB_CHECK(submit_copy(q + LOOKAHEAD));
+    }
+    c->timing = timing_saved;
+    HB_CHECK(condense_finish(k));
+  }
   HB_CHECK(hb_lowrank_solve_compressed(k, k->hbuf[8], k->hbuf[9], k->hbuf[10], k->hbuf[11], k->hbuf[12], k->hbuf[13]));
   if(n) HB_CUDA(cudaMemcpyAsync(dx, k->hbuf[11], sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
   if(meq) HB_CUDA(cudaMemcpyAsync(dyc, k->hbuf[12], sizeof(double) * meq, cudaMemcpyDeviceToHost, c->stream));
@@ -781,7 +868,7 @@ extern "C" int hb_mat_times_vec(hb_ctx* c, int m, long long n, const double* A, 
     HB_LAUNCHED();
   }
   const double b = (c->nranks > 1 && c->rank != 0) ? 0.0 : beta;
-  k_gemv_rows_final<<<(m + 127) / 128, 128, 0, c->stream>>>(m, nchunks, (const double*)c->ws, b, y, alpha);
+  k_gemv_rows_final<<<(m + 31) / 32, 256, 0, c->stream>>>(m, nchunks, (const double*)c->ws, b, y, alpha);
   HB_LAUNCHED();
   if(c->nranks > 1) HB_CHECK(hb_allreduce_sum(c, y, m));
   return HB_OK;

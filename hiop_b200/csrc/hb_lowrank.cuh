@@ -41,6 +41,12 @@ struct hb_lowrank
   // secant memory owned by the engine (hb_secant.cu): S_t, Y_t (lmax x n), previous iterate / gradient / Jacobian
   double *sec_S = nullptr, *sec_Y = nullptr, *sec_xprev = nullptr, *sec_gprev = nullptr, *sec_Jprev = nullptr;
   double sec_L[64 * 64] = {0}, sec_D[64] = {0}; // host copies of L (row-major, stride l) and D; lmax <= 64 in this mode
+  // chunked, copy-overlapped condensation of hb_lowrank_kkt_system_host
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t chunk_ev[32] = {nullptr};
+  double* Ctmp = nullptr;
+  const double** chunk_rowptr_dev = nullptr;
+  const double** chunk_rowptr_host = nullptr; // pinned, 32 x (m + 2 lmax)
   double* Finv = nullptr;  // 16 x 16 inverses of the diagonal of F (cooperative Cholesky / solve)
   bool have_finv = false;
   double* lsq_M = nullptr; // m x m LSQ matrix / Cholesky factor + 2 m-vectors (hb_lsq.cu)

@@ -191,6 +191,28 @@ def test_kkt_system_host_matches_device_path(ctx):
     k.close()
 
 
+def test_kkt_system_host_chunked_overlapped_path(ctx):
+    """Large J: the host entry point uploads J in column chunks on a second stream and condenses chunk by chunk (FP64 DMMA).
+    Same answer as the device-resident path (summation order differs), identical from call to call."""
+    P = synth.make_qn_problem(48000, 700, 6, seed=6)             # 269 MB of J -> above the 256 MB chunking threshold
+    p = _as_dict(P)
+    k, T = _setup_kkt(ctx, p)
+    k.set_condense_mode(0)
+    k.update(T["zl"], T["sxl"], T["zu"], T["sxu"], T["vl"], T["sdl"], T["vu"], T["sdu"])
+    dx, dyc, dyd = _run_solve(ctx, k, p)
+    it = {kk: np.ascontiguousarray(p[kk]) for kk in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu")}
+    outs = []
+    for rep in range(2):
+        hx, hyc, hyd = np.zeros(P.n), np.zeros(P.m_eq), np.zeros(P.m_ineq)
+        k.kkt_system_host(np.ascontiguousarray(P.Jc), np.ascontiguousarray(P.Jd), it, P.rx.copy(), P.ryc.copy(), P.ryd.copy(), hx, hyc, hyd)
+        outs.append((hx, hyc, hyd))
+    for a, b in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(a, b)
+    assert _relerr(outs[0][0], dx) <= 1e-9 and _relerr(outs[0][1], dyc) <= 1e-9 and _relerr(outs[0][2], dyd) <= 1e-9
+    assert k.condense_mode_used() == 0
+    k.close()
+
+
 def test_condense_is_bit_reproducible(ctx):
     P = synth.make_qn_problem(50000, 200, 6, seed=8)
     p = _as_dict(P)
