@@ -143,6 +143,10 @@ def lib() -> ctypes.CDLL:
     f("hb_mds_build_kkt_matrix", c_i, c_vp, *([c_dp] * 17))
     f("hb_mds_hxs_inertia", c_i, c_vp, P(c_i), P(c_i))
     f("hb_mds_solve_compressed", c_i, c_vp, c_vp, *([c_dp] * 6))
+    f("hb_iajaaa_write_matrix_host", c_i, ctypes.c_char_p, c_i, c_dp, c_i, c_i, c_i)
+    f("hb_iajaaa_append_vector_host", c_i, ctypes.c_char_p, c_i, c_dp)
+    f("hb_iajaaa_write_matrix", c_i, c_vp, ctypes.c_char_p, c_i, c_dp, c_i, c_i, c_i)
+    f("hb_iajaaa_append_vector", c_i, c_vp, ctypes.c_char_p, c_i, c_dp)
     f("hb_densekkt_build", c_i, c_vp, c_i, c_i, c_i, c_i, *([c_dp] * 22))
     f("hb_densekkt_solve_compressed", c_i, c_vp, c_vp, c_i, c_i, c_i, c_i, *([c_dp] * 9))
     f("hb_mds_Dx", c_vp, c_vp)

@@ -302,6 +302,14 @@ int hb_densekkt_build(hb_ctx* ctx, int form, int nx, int neq, int nineq, const d
                       double* Dd, double* Msys);
 int hb_densekkt_solve_compressed(hb_ctx* ctx, hb_symdense* s, int form, int nx, int neq, int nineq, const double* rx, const double* rd,
                                  const double* ryc, const double* ryd, double* dx, double* dd, double* dyc, double* dyd, double* work);
+/* ---- write_kkt interchange files (.iajaaa): hiopCSR_IO::writeMatToFile / writeRhsToFile / writeSolToFile
+ * (src/Utils/hiopCSR_IO.hpp:44-155), format in src/LinAlg/csr_iajaaa.md. Byte-compatible with the reference writer. M: N x N
+ * row-major, upper triangle (what build_kkt_matrix leaves in sysMatrix() BEFORE matrixChanged()); vectors are appended one per
+ * line (rhs, then solution, repeatable). *_host take host arrays and need no GPU; the others download from the device. */
+int hb_iajaaa_write_matrix_host(const char* filename, int N, const double* M_host, int nx, int meq, int mineq);
+int hb_iajaaa_append_vector_host(const char* filename, int N, const double* v_host);
+int hb_iajaaa_write_matrix(hb_ctx* ctx, const char* filename, int N, const double* M_dev, int nx, int meq, int mineq);
+int hb_iajaaa_append_vector(hb_ctx* ctx, const char* filename, int N, const double* v_dev);
 const double* hb_mds_Dx(hb_mds* h);
 const double* hb_mds_Hxs(hb_mds* h);
 const double* hb_mds_Dd_inv(hb_mds* h);

@@ -52,6 +52,8 @@ def lib():
         L.ref_densekkt_build.restype = ctypes.c_int
         L.ref_qn_lsq_duals.argtypes = [ctypes.c_void_p, dp, dp, dp]
         L.ref_qn_lsq_duals.restype = ctypes.c_int
+        L.ref_write_iajaaa.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
+        L.ref_write_iajaaa.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -266,6 +268,16 @@ def densekkt_build(form, H, Jc, Jd, it, pat, deltas):
     n_ret = lib().ref_densekkt_build(form, nx, neq, nineq, *[a.ctypes.data_as(dp) for a in keep], DA, M.ctypes.data_as(dp))
     assert n_ret == N
     return M
+
+
+def write_iajaaa(directory, counter, M, nx, meq, mineq, rhs, sol):
+    """hiopCSR_IO writer -> path of kkt_linsys_<counter>.iajaaa inside `directory`."""
+    Ma, pM = _d(M)
+    r, pr = _d(rhs)
+    x, px = _d(sol)
+    rc = lib().ref_write_iajaaa(str(directory).encode(), int(counter), Ma.shape[0], pM, int(nx), int(meq), int(mineq), pr, px)
+    assert rc == 0
+    return os.path.join(str(directory), f"kkt_linsys_{counter}.iajaaa")
 
 
 def bicgstab_dense(A, Minv, b, tol, maxit):

@@ -29,6 +29,8 @@
 #include "hiopKrylovSolver.hpp"
 #include "hiopKKTLinSysDense.hpp"
 #include "hiopDualsUpdater.hpp"
+#include "hiopCSR_IO.hpp"
+#include <unistd.h>
 #include "LinAlgFactory.hpp"
 
 #include <chrono>
@@ -459,6 +461,32 @@ int ref_densekkt_build(int form, int nx, int neq, int nineq, const double* H, co
   }
   delete Jdm; delete Jcm; delete Hm;
   return N;
+}
+
+/// hiopCSR_IO::writeMatToFile + writeRhsToFile + writeSolToFile (src/Utils/hiopCSR_IO.hpp:44-155): writes
+/// <dir>/kkt_linsys_<counter>.iajaaa for the N x N row-major matrix M (upper triangle) and one rhs/solution pair.
+int ref_write_iajaaa(const char* dir, int counter, int N, const double* M, int nx, int meq, int mineq, const double* rhs, const double* sol)
+{
+  static const double one = 1.0;
+  SynthDenseCons iface(1, 0, 0, &one, &one, &one, &one);
+  hiopNlpDenseConstraints nlp(iface);
+  nlp.options->SetIntegerValue("verbosity_level", 0);
+  hiopMatrixDense* Mm = LinearAlgebraFactory::create_matrix_dense("DEFAULT", N, N);
+  memcpy(Mm->local_data(), M, sizeof(double) * (size_t)N * N);
+  hiopVector* r = LinearAlgebraFactory::create_vector("DEFAULT", N);
+  hiopVector* x = LinearAlgebraFactory::create_vector("DEFAULT", N);
+  set_vec(r, rhs); set_vec(x, sol);
+  char cwd[4096];
+  if(!getcwd(cwd, sizeof(cwd)) || chdir(dir) != 0) return -1; // the reference writes into the current directory
+  {
+    hiopCSR_IO io(&nlp);
+    io.writeMatToFile(*Mm, counter, nx, meq, mineq);
+    io.writeRhsToFile(*r, counter);
+    io.writeSolToFile(*x, counter);
+  }
+  int rc = chdir(cwd);
+  delete x; delete r; delete Mm;
+  return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------

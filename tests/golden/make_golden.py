@@ -78,6 +78,22 @@ def densekkt_case():
     print("densekkt rets", int(out["ref_ret0"]), int(out["ref_ret1"]))
 
 
+def iajaaa_case():
+    """write_kkt dump of a small KKT matrix + one rhs/solution pair, written by the reference's hiopCSR_IO."""
+    import shutil
+    import tempfile
+    K = np.triu(synth.make_kkt_like(23, 9, seed=4))
+    K[2, 5] = 0.0
+    K[7, 7] = 1e-30
+    rhs = np.random.default_rng(2).standard_normal(32)
+    sol = np.random.default_rng(3).standard_normal(32) * 1e3
+    with tempfile.TemporaryDirectory() as d:
+        f = ref.write_iajaaa(d, 7, K, 23, 4, 5, rhs, sol)
+        shutil.copy(f, os.path.join(OUT, "kkt_linsys_7.iajaaa"))
+    np.savez_compressed(os.path.join(OUT, "iajaaa_case.npz"), K=K, rhs=rhs, sol=sol, nx=23, meq=4, mineq=5)
+    print("iajaaa golden written")
+
+
 def symdense_cases():
     out = {}
     for i, (nx, m) in enumerate([(24, 9), (70, 30), (3, 0), (1, 1), (130, 61)]):
@@ -160,5 +176,6 @@ if __name__ == "__main__":
         qn_case(*c)
     symdense_cases()
     densekkt_case()
+    iajaaa_case()
     vec_cases()
     mds_case()

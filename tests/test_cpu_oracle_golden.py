@@ -86,6 +86,18 @@ def test_oracle_vector_ops_against_golden():
     assert ko.fraction_to_the_bdry(z, x, 0.995, sel) == float(g["frac_to_bdry_w_sel"])
 
 
+def test_iajaaa_writer_against_reference_golden(tmp_path):
+    """The .iajaaa writer of the C-ABI (host entry points, no GPU needed) reproduces the reference's file byte for byte."""
+    from hiop_b200 import iajaaa
+    g = _load("iajaaa_case.npz")
+    out = str(tmp_path / "k.iajaaa")
+    iajaaa.write_system(out, g["K"], int(g["nx"]), int(g["meq"]), int(g["mineq"]), [(g["rhs"], g["sol"])])
+    gold = os.path.join(os.path.dirname(__file__), "golden", "kkt_linsys_7.iajaaa")
+    assert open(out, "rb").read() == open(gold, "rb").read()
+    back = iajaaa.read_system(gold)
+    assert back["N"] == 32 and len(back["pairs"]) == 1
+
+
 def test_cabi_library_loads_and_exports_every_declared_symbol():
     L = _lib.lib()
     syms = _lib.declared_symbols()

@@ -60,3 +60,27 @@ def test_dense_kkt_against_oracle(ctx, form, nx, neq, nineq, dw, dc):
     K = np.triu(Mo) + np.triu(Mo, 1).T
     assert np.abs(K @ sol - rhs).max() <= 1e-9 * max(1.0, np.abs(rhs).max())
     assert np.abs(sol - f.solve(rhs)).max() <= 1e-8 * max(1.0, np.abs(sol).max())
+
+
+def test_write_kkt_from_device(ctx, tmp_path):
+    """hb_iajaaa_write_matrix / append_vector download from the device and write the reference's interchange format."""
+    import ctypes
+    from hiop_b200 import iajaaa
+    from hiop_b200.engine import KKTLinSysDense, check
+    p = synth.make_mds_problem(0, 40, 6, 9, seed=77)
+    it = dict(zl=p.zl, sxl=p.sxl, zu=p.zu, sxu=p.sxu, vl=p.vl, sdl=p.sdl, vu=p.vu, sdu=p.sdu)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    D = ctx.to_device
+    k = KKTLinSysDense(ctx, 40, 6, 9, "XYcYd")
+    k.build_kkt_matrix(D(p.Hd), D(p.Jcd), D(p.Jdd), {kk: D(v) for kk, v in it.items()}, {kk: D(v) for kk, v in pat.items()},
+                       [D(d) for d in (p.delta_wx, p.delta_wd, p.delta_cc, p.delta_cd)])
+    M = k.Msys()
+    f = str(tmp_path / "kkt_linsys_0.iajaaa").encode()
+    check(ctx.L.hb_iajaaa_write_matrix(ctx.h, f, k.N, ctypes.c_void_p(k.linSys._mptr), 40, 6, 9), "write")
+    rhs = D(np.arange(k.N, dtype=np.float64))
+    check(ctx.L.hb_iajaaa_append_vector(ctx.h, f, k.N, ctypes.c_void_p(rhs.data_ptr())), "append")
+    check(ctx.L.hb_iajaaa_append_vector(ctx.h, f, k.N, ctypes.c_void_p(rhs.data_ptr())), "append")
+    back = iajaaa.read_system(f.decode())
+    assert np.abs(back["M"] - np.triu(M)).max() <= 1e-19 + 1e-15 * np.abs(M).max()
+    assert np.array_equal(back["pairs"][0][0], np.arange(k.N, dtype=np.float64))
+    k.close()

@@ -183,6 +183,26 @@ def test_lsq_duals_match_reference(n, m):
     q.close()
 
 
+def test_iajaaa_writer_is_byte_identical_to_reference(tmp_path):
+    """write_kkt dumps: the C-ABI writer against hiopCSR_IO (matrix + rhs + solution), then the reader round-trips it."""
+    from hiop_b200 import iajaaa
+    K = np.triu(synth.make_kkt_like(23, 9, seed=4))
+    K[2, 5] = 0.0                       # structural zeros are skipped (|a| <= 1e-25)
+    K[7, 7] = 1e-30
+    rhs = np.random.default_rng(2).standard_normal(32)
+    sol = np.random.default_rng(3).standard_normal(32) * 1e3
+    f_ref = ref.write_iajaaa(tmp_path, 7, K, 23, 4, 5, rhs, sol)
+    f_own = str(tmp_path / "own.iajaaa")
+    iajaaa.write_system(f_own, K, 23, 4, 5, [(rhs, sol)])
+    assert open(f_own, "rb").read() == open(f_ref, "rb").read()
+    back = iajaaa.read_system(f_ref)
+    assert (back["N"], back["nx"], back["meq"], back["mineq"]) == (32, 23, 4, 5)
+    Kz = K.copy()
+    Kz[np.abs(Kz) <= 1e-25] = 0.0
+    assert np.abs(back["M"] - Kz).max() <= 1e-19 + 1e-15 * np.abs(Kz).max()          # "%.20f" text: absolute 1e-20 resolution
+    assert np.abs(back["pairs"][0][0] - rhs).max() <= 1e-15 and np.abs(back["pairs"][0][1] - sol).max() <= 1e-12
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
