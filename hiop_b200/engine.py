@@ -264,6 +264,18 @@ class KKTLinSysLowRank:
             self.ctx.sync()
         return ll, sg.value, St, Yt, L[:ll * ll].reshape(ll, ll).copy(), D[:ll].copy()
 
+    def residual_update(self, it: dict, c, d, grad_f, mu, kappa_d, xl, xu, dl, du, crhs, res: dict) -> dict:
+        """hiopResidual::update: fills the 12 residual blocks (device tensors in `res`, keyed by RES_NAMES) from the iterate `it`
+        (device tensors keyed by DIR_NAMES); returns the 11 norms keyed like oracle.kkt_oracle.NORM_NAMES."""
+        I = (ctypes.c_void_p * 12)(*[_ptr(it[k]) for k in DIR_NAMES])
+        R = (ctypes.c_void_p * 12)(*[_ptr(res[k]) for k in RES_NAMES])
+        nrm = (ctypes.c_double * 11)()
+        check(self.ctx.L.hb_lowrank_residual_update(self.h, I, _ptr(c), _ptr(d), _ptr(grad_f), float(mu), float(kappa_d), _ptr(xl), _ptr(xu),
+                                                    _ptr(dl), _ptr(du), _ptr(crhs), R, nrm), "hb_lowrank_residual_update")
+        names = ["inf_nlp_optim", "inf_nlp_feasib", "inf_nlp_complem", "inf_bar_optim", "inf_bar_feasib", "inf_bar_complem", "one_nlp_feasib",
+                 "one_bar_feasib", "one_nlp_optim", "one_bar_optim", "inf_cons_violation"]
+        return dict(zip(names, list(nrm)))
+
     def lsq_duals(self, grad_f, zl, zu, vl, vu, yc, yd) -> bool:
         """hiopDualsLsqUpdate: least-squares yc, yd for the registered Jacobian; False if J J^T + I is not numerically SPD."""
         rc = self.ctx.L.hb_lowrank_lsq_duals(self.h, _ptr(grad_f), _ptr(zl), _ptr(zu), _ptr(vl), _ptr(vu), _ptr(yc), _ptr(yd))

@@ -221,3 +221,16 @@ def make_secant_sequence(n, m_eq, m_ineq, steps=8, seed=31):
                         Jc=Jc0 + 1e-3 * k * rng.standard_normal((m_eq, n)) / np.sqrt(n),
                         Jd=Jd0 + 1e-3 * k * rng.standard_normal((m_ineq, n)) / np.sqrt(n)))
     return seq
+
+
+def make_iterate(p: "QnProblem", seed: int = 61):
+    """A full primal-dual iterate + NLP data around a QnProblem: the 12 blocks of hiopIterate, constraint values, gradient and
+    bounds, as hiopResidual::update consumes them. Slack / dual blocks reuse the problem's (pattern-consistent) ones."""
+    r = np.random.default_rng(seed)
+    n, me, mi = p.n, p.m_eq, p.m_ineq
+    itr = dict(x=r.standard_normal(n), d=r.standard_normal(mi), yc=r.standard_normal(me), yd=r.standard_normal(mi), sxl=p.sxl, sxu=p.sxu,
+               sdl=p.sdl, sdu=p.sdu, zl=p.zl * p.ixl, zu=p.zu * p.ixu, vl=p.vl * p.idl, vu=p.vu * p.idu)
+    data = dict(c=r.standard_normal(me), d=r.standard_normal(mi), grad=r.standard_normal(n), xl=np.where(p.ixl == 1.0, r.standard_normal(n), -1e20),
+                xu=np.where(p.ixu == 1.0, 5.0 + r.standard_normal(n), 1e20), dl=np.where(p.idl == 1.0, r.standard_normal(mi), -1e20),
+                du=np.where(p.idu == 1.0, 0.2 * r.standard_normal(mi), 1e20), crhs=r.standard_normal(me))
+    return itr, data

@@ -189,6 +189,16 @@ int hb_lowrank_secant_reset(hb_lowrank* k, double sigma0, int sigma_strategy);
 int hb_lowrank_secant_update(hb_lowrank* k, const double* x, const double* grad_f, const double* yc, const double* yd,
                              int jacobian_is_constant, int* status);
 int hb_lowrank_secant_state(hb_lowrank* k, int* l, double* sigma, const double** St, const double** Yt, double* L_host, double* D_host);
+/* hiopResidual::update (src/Optimization/hiopResidual.cpp:154-368) with the linear damping terms of hiopLogBarProblem
+ * (hiopLogBarProblem.hpp:135-145): the 12 residual blocks of the current iterate and its 11 norms in one J^T pass + three fused
+ * kernels. it: HOST array of 12 DEVICE pointers {x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu}; cvals (m_eq), dvals (m_ineq) =
+ * constraint bodies, grad_f (n_local), bounds xl, xu (n_local), dl, du (m_ineq), crhs (m_eq); res: 12 DEVICE pointers {rx, rd, ryc,
+ * ryd, rxl, rxu, rdl, rdu, rszl, rszu, rsvl, rsvu} as consumed by hb_lowrank_compute_directions; norms_host (11 doubles) =
+ * nrmInf {nlp_optim, nlp_feasib, nlp_complem, bar_optim, bar_feasib, bar_complem}, nrmOne {nlp_feasib, bar_feasib, nlp_optim,
+ * bar_optim}, nrmInf_cons_violation. Uses the patterns of hb_lowrank_set_patterns and the Jacobian of hb_lowrank_set_jacobian. */
+int hb_lowrank_residual_update(hb_lowrank* k, const double* const* it, const double* cvals, const double* dvals, const double* grad_f, double mu,
+                               double kappa_d, const double* xl, const double* xu, const double* dl, const double* du, const double* crhs,
+                               double* const* res, double* norms_host);
 /* LSQ multiplier (re)computation hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (src/Optimization/hiopDualsUpdater.cpp:
  * 232-332, DPOTRF/DPOTRS :690-735): solves [Jc Jc^T, Jc Jd^T; ., Jd Jd^T + I] [yc; yd] = -[Jc vx; Jd vx + (vl - vu)],
  * vx = grad_f - zl + zu, with the Jacobian registered by hb_lowrank_set_jacobian. J J^T is one pass of the condensation

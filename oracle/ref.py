@@ -54,6 +54,9 @@ def lib():
         L.ref_qn_lsq_duals.restype = ctypes.c_int
         L.ref_write_iajaaa.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp]
         L.ref_write_iajaaa.restype = ctypes.c_int
+        L.ref_qn_residual_update.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, dp,
+                                             ctypes.POINTER(dp), dp]
+        L.ref_qn_residual_update.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -224,6 +227,22 @@ class RefQn:
         rc = lib().ref_qn_lsq_duals(self.h, g.ctypes.data_as(dp), yc.ctypes.data_as(dp), yd.ctypes.data_as(dp))
         assert rc == 0
         return yc[:self.meq].copy(), yd[:self.mineq].copy()
+
+    def residual_update(self, itr: dict, c, d, grad, mu, kappa_d, xl, xu, dl, du, crhs):
+        """hiopResidual::update -> (residual dict, norms dict)."""
+        from .kkt_oracle import RES_NAMES, DIR_NAMES, NORM_NAMES
+        sizes = self._sizes()
+        keep = [np.ascontiguousarray(itr[k] if np.asarray(itr[k]).size else np.zeros(1), dtype=np.float64) for k in DIR_NAMES]
+        IA = (dp * 12)(*[a.ctypes.data_as(dp) for a in keep])
+        rout = [np.zeros(max(sizes[k], 1)) for k in DIR_NAMES]
+        RA = (dp * 12)(*[a.ctypes.data_as(dp) for a in rout])
+        vecs = [np.ascontiguousarray(v if np.asarray(v).size else np.zeros(1), dtype=np.float64) for v in (c, d, grad, xl, xu, dl, du, crhs)]
+        nrm = np.zeros(11)
+        pv = [v.ctypes.data_as(dp) for v in vecs]
+        rc = lib().ref_qn_residual_update(self.h, IA, pv[0], pv[1], pv[2], ctypes.c_double(mu), ctypes.c_double(kappa_d), pv[3], pv[4], pv[5], pv[6],
+                                          pv[7], RA, nrm.ctypes.data_as(dp))
+        assert rc == 0
+        return {rk: rout[i][:sizes[dk]].copy() for i, (rk, dk) in enumerate(zip(RES_NAMES, DIR_NAMES))}, dict(zip(NORM_NAMES, nrm))
 
     def _sizes(self):
         return dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,

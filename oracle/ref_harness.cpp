@@ -30,6 +30,7 @@
 #include "hiopKKTLinSysDense.hpp"
 #include "hiopDualsUpdater.hpp"
 #include "hiopCSR_IO.hpp"
+#include "hiopLogBarProblem.hpp"
 #include <unistd.h>
 #include "LinAlgFactory.hpp"
 
@@ -314,6 +315,39 @@ int ref_qn_lsq_duals(void* h, const double* grad_f, double* yc, double* yd)
   bool ok = base->do_lsq_update(*c->it, *c->gradf, *c->Jc, *c->Jd);
   get_vec(c->it->yc, yc); get_vec(c->it->yd, yd);
   return ok ? 0 : -1;
+}
+
+/// hiopResidual::update (src/Optimization/hiopResidual.cpp:154-368) with the log-barrier proxy hiopLogBarProblem (mu, kappa_d).
+/// iter: 12 blocks in the order x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu; bounds xl, xu (n), dl, du (m_ineq), crhs (m_eq)
+/// overwrite the formulation's own. res: 12 blocks (rx, rd, ryc, ryd, rxl, rxu, rdl, rdu, rszl, rszu, rsvl, rsvu). norms (11):
+/// nrmInf nlp {optim, feasib, complem}, nrmInf bar {optim, feasib, complem}, nrmOne nlp_feasib, bar_feasib, nlp_optim, bar_optim,
+/// nrmInf_cons_violation. Uses the Jacobians planted by ref_qn_set_jac.
+int ref_qn_residual_update(void* h, const double* const* iter, const double* cvals, const double* dvals, const double* grad, double mu,
+                           double kappa_d, const double* xl, const double* xu, const double* dl, const double* du, const double* crhs,
+                           double* const* res, double* norms)
+{
+  QnCtx* c = (QnCtx*)h;
+  hiopIterate& it = *c->it;
+  set_vec(it.x, iter[0]); set_vec(it.d, iter[1]); set_vec(it.yc, iter[2]); set_vec(it.yd, iter[3]);
+  set_vec(it.sxl, iter[4]); set_vec(it.sxu, iter[5]); set_vec(it.sdl, iter[6]); set_vec(it.sdu, iter[7]);
+  set_vec(it.zl, iter[8]); set_vec(it.zu, iter[9]); set_vec(it.vl, iter[10]); set_vec(it.vu, iter[11]);
+  set_vec(c->nlp->xl_, xl); set_vec(c->nlp->xu_, xu); set_vec(c->nlp->dl_, dl); set_vec(c->nlp->du_, du); set_vec(c->nlp->c_rhs_, crhs);
+  hiopVector* cv = c->nlp->alloc_dual_eq_vec();
+  hiopVector* dv = c->nlp->alloc_dual_ineq_vec();
+  set_vec(cv, cvals); set_vec(dv, dvals); set_vec(c->gradf, grad);
+  hiopLogBarProblem lp(c->nlp);
+  lp.mu = mu; lp.kappa_d = kappa_d; lp.iter = &it;
+  hiopResidual r(c->nlp);
+  r.update(it, 0.0, *cv, *dv, *c->gradf, *c->Jc, *c->Jd, lp);
+  get_vec(r.rx, res[0]); get_vec(r.rd, res[1]); get_vec(r.ryc, res[2]); get_vec(r.ryd, res[3]);
+  get_vec(r.rxl, res[4]); get_vec(r.rxu, res[5]); get_vec(r.rdl, res[6]); get_vec(r.rdu, res[7]);
+  get_vec(r.rszl, res[8]); get_vec(r.rszu, res[9]); get_vec(r.rsvl, res[10]); get_vec(r.rsvu, res[11]);
+  norms[0] = r.nrmInf_nlp_optim; norms[1] = r.nrmInf_nlp_feasib; norms[2] = r.nrmInf_nlp_complem;
+  norms[3] = r.nrmInf_bar_optim; norms[4] = r.nrmInf_bar_feasib; norms[5] = r.nrmInf_bar_complem;
+  norms[6] = r.nrmOne_nlp_feasib; norms[7] = r.nrmOne_bar_feasib; norms[8] = r.nrmOne_nlp_optim; norms[9] = r.nrmOne_bar_optim;
+  norms[10] = r.nrmInf_cons_violation;
+  delete dv; delete cv;
+  return 0;
 }
 
 namespace {

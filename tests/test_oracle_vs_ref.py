@@ -203,6 +203,25 @@ def test_iajaaa_writer_is_byte_identical_to_reference(tmp_path):
     assert np.abs(back["pairs"][0][0] - rhs).max() <= 1e-15 and np.abs(back["pairs"][0][1] - sol).max() <= 1e-12
 
 
+@pytest.mark.parametrize("n,m,mz,mu,kd", [(900, 14, True, 0.1, 1e-5), (400, 1, False, 1e-4, 0.0), (300, 9, True, 1.0, 1e-5)])
+def test_residual_update_matches_reference(n, m, mz, mu, kd):
+    """hiopResidual::update: the 12 residual blocks bit for bit (elementwise), J^T y to 1e-13, all 11 norms."""
+    p = synth.make_qn_problem(n, m, 0, masked_zero_divisors=mz)
+    itr, dat = synth.make_iterate(p)
+    q = _ref_system(p)
+    r_r, n_r = q.residual_update(itr, dat["c"], dat["d"], dat["grad"], mu, kd, dat["xl"], dat["xu"], dat["dl"], dat["du"], dat["crhs"])
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    r, nm = ko.residual_update(itr, dat["c"], dat["d"], dat["grad"], p.Jc, p.Jd, mu, kd, pat, dat["xl"], dat["xu"], dat["dl"], dat["du"], dat["crhs"])
+    for k in ko.RES_NAMES:
+        if k == "rx":
+            assert np.abs(r[k] - r_r[k]).max(initial=0.0) <= 1e-13 * max(1.0, np.abs(r_r[k]).max(initial=0.0)), k
+        else:
+            np.testing.assert_array_equal(r[k], r_r[k], err_msg=k)
+    for k in ko.NORM_NAMES:
+        assert abs(nm[k] - n_r[k]) <= 1e-12 * max(1.0, abs(n_r[k])), (k, nm[k], n_r[k])
+    q.close()
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
