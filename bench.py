@@ -112,7 +112,12 @@ def run_reference(args):
         return 0
     cores = os.cpu_count() or 1
     os.environ.setdefault("OPENBLAS_NUM_THREADS", str(cores))
-    n1, n2 = 1500, 3000      # ~2 s of reference CPU work per step
+    # Sample size: ~6 s of reference CPU work per step at (5000, 10000) columns on the GPU box's host; shrunk when many steps are
+    # requested so that the whole run stays within a few minutes. Larger samples extrapolate more faithfully (J no longer fits the
+    # CPU caches), i.e. small samples flatter the reference.
+    nsteps = max(1, args.warmup + args.steps)
+    n2 = int(min(10000, max(2000, 10000 * 150.0 / (6.0 * nsteps))))
+    n1 = n2 // 2
     ts = []
     kind = "reference"
     for i in range(args.warmup + args.steps):
