@@ -179,6 +179,8 @@ int hb_lowrank_set_secant(hb_lowrank* k, int l, double sigma, const double* St, 
  *     sqrt(eps)), appends or shifts the pair into S_t / Y_t, updates L, D and sigma (clamped to [1e-8, 1e8]).
  *     jacobian_is_constant != 0 skips the Jacobian terms (linear constraints; no J_prev is allocated).
  *     *status: 0 first iterate stored, 1 pair accepted, 2 skipped (s too small), 3 skipped (s^T y not positive enough).
+ *     A stored or accepted pair re-installs the memory like hb_lowrank_set_secant does: call hb_lowrank_update afterwards
+ *     (DhInv depends on sigma).
  *   hb_lowrank_secant_state: l, sigma, device pointers of S_t / Y_t (l x n_local row-major), HOST copies of L (l x l) and D. */
 #define HB_SIGMA_STY 1
 #define HB_SIGMA_STY_INV 2
