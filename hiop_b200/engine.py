@@ -276,6 +276,26 @@ class KKTLinSysLowRank:
                  "one_bar_feasib", "one_nlp_optim", "one_bar_optim", "inf_cons_violation"]
         return dict(zip(names, list(nrm)))
 
+    # ---- hiopIterate / hiopLogBarProblem: the line-search side of an iteration ----
+    def _blocks(self, d: dict):
+        return (ctypes.c_void_p * 12)(*[_ptr(d[k]) for k in DIR_NAMES])
+
+    def fraction_to_bdry(self, it: dict, direction: dict, tau: float):
+        ap, ad = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        check(self.ctx.L.hb_iterate_fraction_to_bdry(self.h, self._blocks(it), self._blocks(direction), float(tau), ctypes.byref(ap), ctypes.byref(ad)),
+              "hb_iterate_fraction_to_bdry")
+        return ap.value, ad.value
+
+    def take_step(self, it: dict, direction: dict, alpha_primal: float, alpha_dual: float, out: dict, which: int = 3):
+        check(self.ctx.L.hb_iterate_take_step(self.h, self._blocks(it), self._blocks(direction), float(alpha_primal), float(alpha_dual), int(which),
+                                              self._blocks(out)), "hb_iterate_take_step")
+
+    def logbar(self, it: dict, f: float, mu: float, kappa_d: float, grad_f=None, grad_x=None, grad_d=None) -> float:
+        fl = ctypes.c_double(0.0)
+        check(self.ctx.L.hb_iterate_logbar(self.h, self._blocks(it), float(f), float(mu), float(kappa_d), _ptr(grad_f), _ptr(grad_x), _ptr(grad_d),
+                                           ctypes.byref(fl)), "hb_iterate_logbar")
+        return fl.value
+
     def lsq_duals(self, grad_f, zl, zu, vl, vu, yc, yd) -> bool:
         """hiopDualsLsqUpdate: least-squares yc, yd for the registered Jacobian; False if J J^T + I is not numerically SPD."""
         rc = self.ctx.L.hb_lowrank_lsq_duals(self.h, _ptr(grad_f), _ptr(zl), _ptr(zu), _ptr(vl), _ptr(vu), _ptr(yc), _ptr(yd))

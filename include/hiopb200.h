@@ -201,6 +201,21 @@ int hb_lowrank_secant_state(hb_lowrank* k, int* l, double* sigma, const double**
 int hb_lowrank_residual_update(hb_lowrank* k, const double* const* it, const double* cvals, const double* dvals, const double* grad_f, double mu,
                                double kappa_d, const double* xl, const double* xu, const double* dl, const double* du, const double* crhs,
                                double* const* res, double* norms_host);
+/* Line-search side of one IPM iteration (hiopIterate / hiopLogBarProblem). it / dir / out: HOST arrays of 12 DEVICE pointers in the
+ * iterate order {x, d, yc, yd, sxl, sxu, sdl, sdu, zl, zu, vl, vu}; patterns from hb_lowrank_set_patterns.
+ *   hb_iterate_fraction_to_bdry: hiopIterate::fractionToTheBdry (hiopIterate.cpp:326-363): largest alpha_primal (slacks) and alpha_dual
+ *     (bound duals) with s + alpha ds >= (1 - tau) s; eight reductions of the reference in two fused passes.
+ *   hb_iterate_take_step: takeStep_primals (which & 1: x, d) / takeStep_duals (which & 2: yc, yd with alpha_primal; zl, zu, vl, vu
+ *     with alpha_dual) (:366-390); out may alias it.
+ *   hb_iterate_logbar: hiopLogBarProblem::updateWithNlpInfo (hiopLogBarProblem.hpp:83-120): f_logbar = f - mu sum log(slacks) +
+ *     kappa_d mu sum (one-sided slacks), grad_x_logbar = grad_f - mu/sxl + mu/sxu + kappa_d mu (ixl - ixu), grad_d_logbar likewise;
+ *     with both gradient pointers NULL it is updateWithNlpInfo_trial_funcOnly (:121-132, function value only). */
+int hb_iterate_fraction_to_bdry(hb_lowrank* k, const double* const* it, const double* const* dir, double tau, double* alpha_primal,
+                                double* alpha_dual);
+int hb_iterate_take_step(hb_lowrank* k, const double* const* it, const double* const* dir, double alpha_primal, double alpha_dual, int which,
+                         double* const* out);
+int hb_iterate_logbar(hb_lowrank* k, const double* const* it, double f, double mu, double kappa_d, const double* grad_f, double* grad_x_logbar,
+                      double* grad_d_logbar, double* f_logbar);
 /* LSQ multiplier (re)computation hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (src/Optimization/hiopDualsUpdater.cpp:
  * 232-332, DPOTRF/DPOTRS :690-735): solves [Jc Jc^T, Jc Jd^T; ., Jd Jd^T + I] [yc; yd] = -[Jc vx; Jd vx + (vl - vu)],
  * vx = grad_f - zl + zu, with the Jacobian registered by hb_lowrank_set_jacobian. J J^T is one pass of the condensation

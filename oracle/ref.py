@@ -57,6 +57,10 @@ def lib():
         L.ref_qn_residual_update.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), dp, dp, dp, ctypes.c_double, ctypes.c_double, dp, dp, dp, dp, dp,
                                              ctypes.POINTER(dp), dp]
         L.ref_qn_residual_update.restype = ctypes.c_int
+        L.ref_qn_logbar_update.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.c_double, ctypes.c_double, ctypes.c_double, dp, dp, dp, dp]
+        L.ref_qn_logbar_update.restype = ctypes.c_int
+        L.ref_qn_fraction_to_bdry.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ctypes.c_double, dp, dp]
+        L.ref_qn_fraction_to_bdry.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -243,6 +247,27 @@ class RefQn:
                                           pv[7], RA, nrm.ctypes.data_as(dp))
         assert rc == 0
         return {rk: rout[i][:sizes[dk]].copy() for i, (rk, dk) in enumerate(zip(RES_NAMES, DIR_NAMES))}, dict(zip(NORM_NAMES, nrm))
+
+    def _blocks(self, d: dict):
+        from .kkt_oracle import DIR_NAMES
+        keep = [np.ascontiguousarray(d[k] if np.asarray(d[k]).size else np.zeros(1), dtype=np.float64) for k in DIR_NAMES]
+        return keep, (dp * 12)(*[a.ctypes.data_as(dp) for a in keep])
+
+    def logbar_update(self, itr: dict, f, mu, kappa_d, grad):
+        """hiopLogBarProblem::updateWithNlpInfo -> (f_logbar, grad_x_logbar, grad_d_logbar)."""
+        keep, IA = self._blocks(itr)
+        g = np.ascontiguousarray(grad, dtype=np.float64)
+        gx, gd, fl = np.zeros(self.n), np.zeros(max(self.mineq, 1)), np.zeros(1)
+        lib().ref_qn_logbar_update(self.h, IA, ctypes.c_double(f), ctypes.c_double(mu), ctypes.c_double(kappa_d), g.ctypes.data_as(dp),
+                                   gx.ctypes.data_as(dp), gd.ctypes.data_as(dp), fl.ctypes.data_as(dp))
+        return float(fl[0]), gx, gd[:self.mineq].copy()
+
+    def fraction_to_bdry(self, itr: dict, direction: dict, tau):
+        k1, IA = self._blocks(itr)
+        k2, DA = self._blocks(direction)
+        a = np.zeros(2)
+        lib().ref_qn_fraction_to_bdry(self.h, IA, DA, ctypes.c_double(tau), a[:1].ctypes.data_as(dp), a[1:].ctypes.data_as(dp))
+        return float(a[0]), float(a[1])
 
     def _sizes(self):
         return dict(x=self.n, d=self.mineq, yc=self.meq, yd=self.mineq, sxl=self.n, sxu=self.n, sdl=self.mineq,

@@ -351,6 +351,44 @@ int ref_qn_residual_update(void* h, const double* const* iter, const double* cva
 }
 
 namespace {
+void plant_iterate(hiopIterate& it, const double* const* b)
+{
+  set_vec(it.x, b[0]); set_vec(it.d, b[1]); set_vec(it.yc, b[2]); set_vec(it.yd, b[3]);
+  set_vec(it.sxl, b[4]); set_vec(it.sxu, b[5]); set_vec(it.sdl, b[6]); set_vec(it.sdu, b[7]);
+  set_vec(it.zl, b[8]); set_vec(it.zu, b[9]); set_vec(it.vl, b[10]); set_vec(it.vu, b[11]);
+}
+} // namespace
+
+/// hiopLogBarProblem::updateWithNlpInfo (hiopLogBarProblem.hpp:83-120): log-barrier function value and gradients at the iterate.
+int ref_qn_logbar_update(void* h, const double* const* iter, double f, double mu, double kappa_d, const double* grad, double* gx, double* gd,
+                         double* f_logbar)
+{
+  QnCtx* c = (QnCtx*)h;
+  plant_iterate(*c->it, iter);
+  set_vec(c->gradf, grad);
+  hiopVector* cv = c->nlp->alloc_dual_eq_vec();
+  hiopVector* dv = c->nlp->alloc_dual_ineq_vec();
+  hiopLogBarProblem lp(c->nlp);
+  lp.kappa_d = kappa_d;
+  lp.updateWithNlpInfo(*c->it, mu, f, *cv, *dv, *c->gradf, *c->Jc, *c->Jd);
+  get_vec(lp._grad_x_logbar, gx); get_vec(lp._grad_d_logbar, gd);
+  *f_logbar = lp.f_logbar;
+  delete dv; delete cv;
+  return 0;
+}
+
+/// hiopIterate::fractionToTheBdry (hiopIterate.cpp:326-363): largest primal / dual step lengths keeping slacks and duals positive.
+int ref_qn_fraction_to_bdry(void* h, const double* const* iter, const double* const* dir, double tau, double* alpha_primal, double* alpha_dual)
+{
+  QnCtx* c = (QnCtx*)h;
+  plant_iterate(*c->it, iter);
+  hiopIterate d(c->nlp);
+  plant_iterate(d, dir);
+  c->it->fractionToTheBdry(d, tau, *alpha_primal, *alpha_dual);
+  return 0;
+}
+
+namespace {
 void ensure_pert(QnCtx* c)
 {
   if(c->pert) return;

@@ -1,0 +1,51 @@
+"""hiopIterate / hiopLogBarProblem vector pipeline on the device: fraction-to-the-boundary, step, log-barrier function
+and gradients, against the oracle restatement (pinned to the reference by
+tests/test_oracle_vs_ref.py::test_logbar_and_fraction_to_bdry_match_reference)."""
+import numpy as np
+import pytest
+
+from hiop_b200 import synth
+from oracle import kkt_oracle as ko
+from test_gpu_parity import ctx, _setup_kkt, _as_dict  # noqa: F401
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,m,mz,mu,kd", [(20000, 40, True, 0.1, 1e-5), (4099, 37, False, 1e-4, 0.0), (3000, 1, True, 1.0, 1e-5), (2500, 0, False, 0.5, 1e-5)])
+def test_line_search_pipeline_against_oracle(ctx, n, m, mz, mu, kd):
+    P = synth.make_qn_problem(n, m, 0, masked_zero_divisors=mz, seed=23 + n)
+    p = _as_dict(P)
+    itr, dat = synth.make_iterate(P)
+    pat = dict(ixl=P.ixl, ixu=P.ixu, idl=P.idl, idu=P.idu)
+    for s, ptn in (("sxl", "ixl"), ("sxu", "ixu"), ("sdl", "idl"), ("sdu", "idu")):
+        itr[s] = np.where(pat[ptn] == 1.0, np.abs(itr[s]) + 1e-3, itr[s])
+    rng = np.random.default_rng(5)
+    direction = {kk: rng.standard_normal(np.asarray(v).size) * np.where(np.asarray(v) != 0, 1.0, 0.0) for kk, v in itr.items()}
+    k, T = _setup_kkt(ctx, p)
+    D = ctx.to_device
+    it_d = {kk: D(np.ascontiguousarray(v)) for kk, v in itr.items()}
+    dir_d = {kk: D(np.ascontiguousarray(v)) for kk, v in direction.items()}
+    # fraction to the boundary: exact (a minimum of identically computed quotients)
+    ap, ad = k.fraction_to_bdry(it_d, dir_d, 0.995)
+    apo, ado = ko.iterate_fraction_to_bdry(itr, direction, 0.995, pat)
+    assert (ap, ad) == (apo, ado)
+    # trial point
+    out_d = {kk: ctx.zeros(np.asarray(v).size) for kk, v in itr.items()}
+    k.take_step(it_d, dir_d, ap, ad, out_d)
+    ctx.sync()
+    for kk in ko.DIR_NAMES:
+        al = ap if kk in ("x", "d", "yc", "yd") else ad
+        if kk in ("sxl", "sxu", "sdl", "sdu"):
+            continue                                 # slacks are recomputed from x, d by the driver (hiopIterate.cpp:270-303)
+        want = itr[kk] + al * direction[kk]
+        assert np.abs(out_d[kk].cpu().numpy() - want).max(initial=0.0) <= 1e-15 * max(1.0, np.abs(want).max(initial=0.0)), kk
+    # log-barrier function + gradients, and the function-only variant
+    gx, gd = ctx.zeros(n), ctx.zeros(P.m_ineq)
+    fl = k.logbar(it_d, 3.25, mu, kd, D(dat["grad"]), gx, gd)
+    flo, gxo, gdo = ko.logbar_update(itr, 3.25, mu, kd, dat["grad"], pat)
+    ctx.sync()
+    assert abs(fl - flo) <= 1e-12 * max(1.0, abs(flo))
+    np.testing.assert_array_equal(gx.cpu().numpy(), gxo)
+    np.testing.assert_array_equal(gd.cpu().numpy(), gdo)
+    assert k.logbar(it_d, 3.25, mu, kd) == fl
+    k.close()

@@ -222,6 +222,29 @@ def test_residual_update_matches_reference(n, m, mz, mu, kd):
     q.close()
 
 
+@pytest.mark.parametrize("n,m,mz,mu,kd", [(900, 14, True, 0.1, 1e-5), (400, 1, False, 1e-4, 0.0)])
+def test_logbar_and_fraction_to_bdry_match_reference(n, m, mz, mu, kd):
+    """hiopLogBarProblem::updateWithNlpInfo and hiopIterate::fractionToTheBdry."""
+    p = synth.make_qn_problem(n, m, 0, masked_zero_divisors=mz)
+    itr, dat = synth.make_iterate(p)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    # slacks must be positive where the pattern is set (log): masked-out entries may be anything
+    for s, ptn in (("sxl", "ixl"), ("sxu", "ixu"), ("sdl", "idl"), ("sdu", "idu")):
+        itr[s] = np.where(pat[ptn] == 1.0, np.abs(itr[s]) + 1e-3, itr[s])
+    q = _ref_system(p)
+    fl_r, gx_r, gd_r = q.logbar_update(itr, 3.25, mu, kd, dat["grad"])
+    fl, gx, gd = ko.logbar_update(itr, 3.25, mu, kd, dat["grad"], pat)
+    assert abs(fl - fl_r) <= 1e-13 * max(1.0, abs(fl_r))
+    np.testing.assert_array_equal(gx, gx_r)
+    np.testing.assert_array_equal(gd, gd_r)
+    rng = np.random.default_rng(12)
+    direction = {k: rng.standard_normal(np.asarray(v).size) * np.where(np.asarray(v) != 0, 1.0, 0.0) for k, v in itr.items()}
+    ap_r, ad_r = q.fraction_to_bdry(itr, direction, 0.995)
+    ap, ad = ko.iterate_fraction_to_bdry(itr, direction, 0.995, pat)
+    assert ap == ap_r and ad == ad_r, ((ap, ad), (ap_r, ad_r))
+    q.close()
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
