@@ -367,6 +367,7 @@ def run_engine(args):
             ms_total = float(t.item())
         ms_step = ms_total / args.steps
         nref, resid = k.last_solve_stats()
+        mode = k.condense_mode_used()      # of the timed loop (the host-buffer path below condenses with the FP64 kernel)
 
         # ---- parity gate of SURVEY 8(d), outside the timed region: relative residual of the 3-block compressed KKT system of the
         # last step, evaluated with FP64 operators that do not depend on the condensed matrix or its factor (compact-form B*x +
@@ -425,7 +426,6 @@ def run_engine(args):
     Ma = m + 2 * l
     syrk = statistics.mean(syrk_ms)
     fl = flops_syrk(n_local, Ma)
-    mode = k.condense_mode_used()
     if mode == 0:
         achieved = fl / (syrk * 1e-3) / 1e12
         roofline = {"kernel": "k_syrk_ws (FP64 DMMA.8x8x4 condensation [J;S;Y] DhInv [J;S;Y]^T)", "bound": "tensor", "achieved": achieved,
