@@ -37,8 +37,32 @@ def _worker(rank, world, uid, n, m, l, out):
     out[f"dx{rank}"] = dx.cpu().numpy()
     out[f"dy{rank}"] = np.concatenate([dyc.cpu().numpy(), dyd.cpu().numpy()])
     out[f"N{rank}"] = k.N()
-    # reductions through the vector API: global dot / inf-norm
-    out[f"dot{rank}"] = ctx.vec_dot(T["rx"], T["rx"]) if False else 0.0
+    # the sharded entry points around the solve: device BiCGStab (compound-vector reductions count replicated blocks once),
+    # residual norms, fraction-to-the-boundary, LSQ multipliers
+    nb = {"x", "sxl", "sxu", "zl", "zu"}
+    shard = lambda name, v: np.ascontiguousarray(v[sl]) if name in nb else np.ascontiguousarray(v)
+    res = {rk: D(shard(dk, P.res[rk])) for rk, dk in zip(ko.RES_NAMES, ko.DIR_NAMES)}
+    dirs = {dk: ctx.zeros(res[rk].numel()) for rk, dk in zip(ko.RES_NAMES, ko.DIR_NAMES)}
+    ok, info = k.compute_directions_w_IR(res, dirs, mu=1e-2, maxit=8)
+    assert ok
+    ctx.sync()
+    out[f"ir_info{rank}"] = tuple(info)
+    for dk in ko.DIR_NAMES:
+        out[f"ir_{dk}{rank}"] = dirs[dk].cpu().numpy()
+    itr, dat = synth.make_iterate(P)
+    it_d = {dk: D(shard(dk, v)) for dk, v in itr.items()}
+    xl, xu = D(np.ascontiguousarray(dat["xl"][sl])), D(np.ascontiguousarray(dat["xu"][sl]))
+    res2 = {rk: ctx.zeros(it_d[dk].numel()) for rk, dk in zip(ko.RES_NAMES, ko.DIR_NAMES)}
+    nm = k.residual_update(it_d, D(dat["c"]), D(dat["d"]), D(np.ascontiguousarray(dat["grad"][sl])), 0.1, 1e-5, xl, xu, D(dat["dl"]), D(dat["du"]),
+                           D(dat["crhs"]), res2)
+    out[f"norms{rank}"] = nm
+    rng = np.random.default_rng(5)
+    direction = {dk: rng.standard_normal(np.asarray(v).size) * np.where(np.asarray(v) != 0, 1.0, 0.0) for dk, v in itr.items()}
+    out[f"ftb{rank}"] = k.fraction_to_bdry(it_d, {dk: D(shard(dk, v)) for dk, v in direction.items()}, 0.995)
+    yc, yd = ctx.zeros(P.m_eq), ctx.zeros(P.m_ineq)
+    assert k.lsq_duals(D(np.ascontiguousarray(dat["grad"][sl])), T["zl"], T["zu"], T["vl"], T["vu"], yc, yd)
+    ctx.sync()
+    out[f"lsq{rank}"] = np.concatenate([yc.cpu().numpy(), yd.cpu().numpy()])
     k.close()
     ctx.close()
 
@@ -64,3 +88,25 @@ def test_two_gpu_sharded_matches_oracle(n, m, l):
     dxs = np.concatenate([out["dx0"], out["dx1"]])
     assert np.abs(dxs - dx).max() <= 1e-8 * np.abs(dx).max()
     assert np.abs(out["dy0"] - np.concatenate([dyc, dyd])).max() <= 1e-8 * max(1.0, np.abs(dyc).max())
+    # sharded entry points around the solve
+    it = dict(sxl=P.sxl, sxu=P.sxu, zl=P.zl, zu=P.zu, sdl=P.sdl, sdu=P.sdu, vl=P.vl, vu=P.vu)
+    pat = dict(ixl=P.ixl, ixu=P.ixu, idl=P.idl, idu=P.idu)
+    do, info_o = ko.compute_directions_w_ir(st, it, pat, P.res, 1e-2, 8, Dx=Dx)
+    assert out["ir_info0"][0] == out["ir_info1"][0] == info_o[0] and out["ir_info0"][1] == info_o[1]
+    nb = {"x", "sxl", "sxu", "zl", "zu"}
+    for dk in ko.DIR_NAMES:
+        got = np.concatenate([out[f"ir_{dk}0"], out[f"ir_{dk}1"]]) if dk in nb else out[f"ir_{dk}0"]
+        if dk not in nb:
+            np.testing.assert_array_equal(out[f"ir_{dk}0"], out[f"ir_{dk}1"])
+        assert np.abs(got - do[dk]).max(initial=0.0) <= 1e-8 * max(1.0, np.abs(do[dk]).max(initial=0.0)), dk
+    itr, dat = synth.make_iterate(P)
+    _, no = ko.residual_update(itr, dat["c"], dat["d"], dat["grad"], P.Jc, P.Jd, 0.1, 1e-5, pat, dat["xl"], dat["xu"], dat["dl"], dat["du"], dat["crhs"])
+    for kk in ko.NORM_NAMES:
+        assert out["norms0"][kk] == out["norms1"][kk]
+        assert abs(out["norms0"][kk] - no[kk]) <= 1e-12 * max(1.0, abs(no[kk])), kk
+    rng = np.random.default_rng(5)
+    direction = {dk: rng.standard_normal(np.asarray(v).size) * np.where(np.asarray(v) != 0, 1.0, 0.0) for dk, v in itr.items()}
+    assert out["ftb0"] == out["ftb1"] == ko.iterate_fraction_to_bdry(itr, direction, 0.995, pat)
+    yco, ydo = ko.lsq_duals(P.Jc, P.Jd, dat["grad"], P.zl, P.zu, P.vl, P.vu)
+    np.testing.assert_array_equal(out["lsq0"], out["lsq1"])
+    assert np.abs(out["lsq0"] - np.concatenate([yco, ydo])).max() <= 1e-9 * max(1.0, np.abs(np.concatenate([yco, ydo])).max())
