@@ -107,6 +107,40 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     assert b"sm_100a" in L.hb_version()
 
 
+def test_ctypes_prototypes_match_the_header():
+    """Every function of include/hiopb200.h has a ctypes prototype with the same number of parameters and a compatible scalar /
+    pointer kind per position (a wrong count or a double passed where the C side expects a pointer would only show up on a GPU)."""
+    import ctypes
+    import re
+    L = _lib.lib()
+    txt = re.sub(r"/\*.*?\*/", "", open(_lib.HEADER_PATH).read(), flags=re.S)
+    protos = re.findall(r"\b(?:int|long long|double|const char\*|const double\*|void)\s*\*?\s*(hb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S)
+    assert len(protos) >= 90
+    bad = []
+    for name, params in protos:
+        params = " ".join(params.split())
+        plist = [] if params in ("", "void") else [q.strip() for q in params.split(",")]
+        fn = getattr(L, name)
+        if fn.argtypes is None:
+            bad.append((name, "no ctypes prototype"))
+            continue
+        if len(fn.argtypes) != len(plist):
+            bad.append((name, f"header has {len(plist)} parameters, ctypes {len(fn.argtypes)}"))
+            continue
+        for i, (cdecl, at) in enumerate(zip(plist, fn.argtypes)):
+            is_ptr_c = "*" in cdecl
+            is_ptr_py = at in (ctypes.c_void_p, ctypes.c_char_p) or hasattr(at, "contents") or issubclass(at, ctypes._Pointer)
+            if is_ptr_c != is_ptr_py:
+                bad.append((name, f"parameter {i} '{cdecl}' vs {at.__name__}"))
+            elif not is_ptr_c:
+                want = ctypes.c_double if cdecl.split()[0] == "double" else None
+                if want is not None and at is not ctypes.c_double:
+                    bad.append((name, f"parameter {i} '{cdecl}' vs {at.__name__}"))
+                if want is None and at is ctypes.c_double:
+                    bad.append((name, f"parameter {i} '{cdecl}' vs {at.__name__}"))
+    assert not bad, bad
+
+
 def test_engine_fails_loudly_without_gpu():
     import ctypes
     import torch
