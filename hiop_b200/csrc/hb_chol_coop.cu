@@ -481,6 +481,35 @@ k_spd_solve_coop(const double* __restrict__ F, int ldf, int N, const double* __r
   }
 }
 
+// 16 x 16 inverses of the diagonal triangles of an existing factor (the multi-launch Cholesky for N > 2048 does not produce them):
+// one CTA per 64-block, thread (sb, c) builds column c of T_sb^-1 right-looking like factor_diag does.
+__global__ void __launch_bounds__(64)
+k_diag_inverses(const double* __restrict__ F, int ldf, int N, double* __restrict__ invd)
+{
+  __shared__ double T[4][16][17];
+  const int k0 = blockIdx.x * CB, tid = threadIdx.x, sb = tid >> 4, c = tid & 15;
+  for(int e = tid; e < 4 * 256; e += 64) {
+    const int s = e >> 8, r = (e >> 4) & 15, q = e & 15;
+    const int gi = k0 + s * 16 + r, gj = k0 + s * 16 + q;
+    T[s][r][q] = (gi < N && gj < N && r >= q) ? LC(F, ldf, gi, gj) : (r == q ? 1.0 : 0.0); // identity beyond N, as the padded panels
+  }
+  __syncthreads();
+  double x[16], sacc[16];
+#pragma unroll
+  for(int r = 0; r < 16; r++) { x[r] = 0.0; sacc[r] = 0.0; }
+#pragma unroll
+  for(int q = 0; q < 16; q++) {
+    const double rq = 1.0 / T[sb][q][q];
+    if(q == c) x[q] = rq;
+    else if(q > c) x[q] = -sacc[q] * rq;
+#pragma unroll
+    for(int r = q + 1; r < 16; r++) sacc[r] += T[sb][r][q] * x[q];
+  }
+  double* inv = invd + (size_t)blockIdx.x * (4 * 16 * 17) + sb * 16 * 17;
+#pragma unroll
+  for(int r = 0; r < 16; r++) inv[r * 17 + c] = x[r];
+}
+
 bool g_coop_checked = false, g_coop_ok = false;
 int g_coop_max_ctas = 0;
 
@@ -490,7 +519,6 @@ int g_coop_max_ctas = 0;
 int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* used)
 {
   *used = false;
-  if(N <= CB || N > 2048) return HB_OK;
   if(!g_coop_checked) {
     g_coop_checked = true;
     const char* e = getenv("HB_CHOL_COOP");
@@ -507,7 +535,7 @@ int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, doub
       cudaGetLastError();
     }
   }
-  if(!g_coop_ok) return HB_OK;
+  if(!g_coop_ok || N <= CB || N > 2048) return HB_OK;
   // one CTA per trailing tile of the first panel (the widest step), never more than fit on the device at once
   const int nt0 = (N - CB + CB - 1) / CB;
   int G = nt0 * (nt0 + 1) / 2;
@@ -522,12 +550,27 @@ int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, doub
   return HB_OK;
 }
 
+// fills invd for a factor produced by any Cholesky path
+int hb_dense_chol_diag_inverses(hb_ctx* c, int N, const double* F, int ldf, double* invd)
+{
+  if(N <= 0) return HB_OK;
+  k_diag_inverses<<<(N + CB - 1) / CB, 64, 0, c->stream>>>(F, ldf, N, invd);
+  HB_LAUNCHED();
+  return HB_OK;
+}
+bool hb_dense_coop_available(hb_ctx* c)
+{
+  bool used = false;
+  hb_dense_chol_coop(c, 0, nullptr, 0, nullptr, nullptr, &used); // runs the one-time capability check
+  return g_coop_ok;
+}
+
 // cooperative solve + refinement; invd must come from hb_dense_chol_coop of the same factor. work: 2N+2 doubles.
 int hb_dense_spd_solve_coop(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
                             const double* rhs, double* x, double* work, double tol, int max_refine, double* stats_dev, bool* used)
 {
   *used = false;
-  if(!g_coop_ok || !invd || N <= CB || N > 2048) return HB_OK;
+  if(!g_coop_ok || !invd || N <= CB || N > 16384) return HB_OK;
   static bool attr = false;
   static int max_ctas = 0;
   if(!attr) {

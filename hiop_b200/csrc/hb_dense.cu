@@ -746,6 +746,8 @@ constexpr size_t TRAILING_SMEM = sizeof(double) * 2 * NB * TLD;
 static bool g_trailing_attr = false;
 
 int hb_dense_chol_coop(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* used);
+int hb_dense_chol_diag_inverses(hb_ctx* c, int N, const double* F, int ldf, double* invd);
+bool hb_dense_coop_available(hb_ctx* c);
 int hb_dense_spd_solve_coop(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
                             const double* rhs, double* x, double* work, double tol, int max_refine, double* stats_dev, bool* used);
 
@@ -838,7 +840,12 @@ int hb_dense_chol_with_inverses(hb_ctx* c, int N, double* A, int lda, int* info_
   *have_inv = false;
   HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, invd, have_inv));
   if(*have_inv) return HB_OK;
-  return hb_dense_factor_blocked(c, N, A, lda, false, nullptr, info_dev);
+  HB_CHECK(hb_dense_factor_blocked(c, N, A, lda, false, nullptr, info_dev));
+  if(N > 64 && invd && hb_dense_coop_available(c)) { // large N: multi-launch factor, but the solve can still be cooperative
+    HB_CHECK(hb_dense_chol_diag_inverses(c, N, A, lda, invd));
+    *have_inv = true;
+  }
+  return HB_OK;
 }
 
 int hb_dense_spd_solve_refine2(hb_ctx* c, int N, const double* F, int ldf, const double* invd, const double* s, const double* Nref, int ldn,
