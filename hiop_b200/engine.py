@@ -266,7 +266,7 @@ class KKTLinSysLowRank:
 
     def residual_update(self, it: dict, c, d, grad_f, mu, kappa_d, xl, xu, dl, du, crhs, res: dict) -> dict:
         """hiopResidual::update: fills the 12 residual blocks (device tensors in `res`, keyed by RES_NAMES) from the iterate `it`
-        (device tensors keyed by DIR_NAMES); returns the 11 norms keyed like oracle.kkt_oracle.NORM_NAMES."""
+        (device tensors keyed by DIR_NAMES); returns the 11 norms as a dict (inf_nlp_optim ... inf_cons_violation, see include/hiopb200.h)."""
         I = (ctypes.c_void_p * 12)(*[_ptr(it[k]) for k in DIR_NAMES])
         R = (ctypes.c_void_p * 12)(*[_ptr(res[k]) for k in RES_NAMES])
         nrm = (ctypes.c_double * 11)()
