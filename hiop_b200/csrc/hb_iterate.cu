@@ -124,6 +124,28 @@ k_take_step(StepArgs A)
   }
 }
 
+// hiopVectorPar::adjustDuals_plh (src/LinAlg/hiopVectorPar.cpp:1117-1148): keep z within [mu/(kappa s), kappa mu/s] on the pattern
+__device__ __forceinline__ double adjust_plh(double z, double s, double sel, double mu, double kappa)
+{
+  if(sel != 1.0) return z;
+  double a = __ddiv_rn(mu, s);
+  const double b = __ddiv_rn(a, kappa);
+  a = __dmul_rn(a, kappa);
+  if(z < b) return b;
+  if(a <= b) return b;
+  return a < z ? a : z;
+}
+__global__ void __launch_bounds__(ET)
+k_adjust_duals(long long n, double mu, double kappa, const double* __restrict__ sl, const double* __restrict__ su, const double* __restrict__ il,
+               const double* __restrict__ iu, double* __restrict__ zl, double* __restrict__ zu)
+{
+  const long long stride = (long long)gridDim.x * ET;
+  for(long long i = (long long)blockIdx.x * ET + threadIdx.x; i < n; i += stride) {
+    zl[i] = adjust_plh(zl[i], sl[i], il[i], mu, kappa);
+    zu[i] = adjust_plh(zu[i], su[i], iu[i], mu, kappa);
+  }
+}
+
 inline int grid_for(hb_ctx* c, long long n)
 {
   long long g = (n + ET - 1) / ET;
@@ -197,6 +219,22 @@ extern "C" int hb_iterate_take_step(hb_lowrank* k, const double* const* it, cons
     const int ids[6] = {YD, YC, ZL, ZU, VL, VU};
     const double al[6] = {alpha_primal, alpha_primal, alpha_dual, alpha_dual, alpha_dual, alpha_dual};
     HB_CHECK(launch(ids, al, 6));
+  }
+  return HB_OK;
+}
+
+extern "C" int hb_iterate_adjust_duals_plh(hb_lowrank* k, double* const* it, double mu, double kappa_sigma)
+{
+  HB_REQUIRE(k && it, "hb_iterate_adjust_duals_plh: null argument");
+  HB_REQUIRE(k->n == 0 || k->ixl, "hb_iterate_adjust_duals_plh: patterns not set");
+  hb_ctx* c = k->ctx;
+  if(k->n > 0) {
+    k_adjust_duals<<<grid_for(c, k->n), ET, 0, c->stream>>>(k->n, mu, kappa_sigma, it[SXL], it[SXU], k->ixl, k->ixu, it[ZL], it[ZU]);
+    HB_LAUNCHED();
+  }
+  if(k->mineq > 0) {
+    k_adjust_duals<<<grid_for(c, k->mineq), ET, 0, c->stream>>>(k->mineq, mu, kappa_sigma, it[SDL], it[SDU], k->idl, k->idu, it[VL], it[VU]);
+    HB_LAUNCHED();
   }
   return HB_OK;
 }

@@ -290,6 +290,10 @@ class KKTLinSysLowRank:
         check(self.ctx.L.hb_iterate_take_step(self.h, self._blocks(it), self._blocks(direction), float(alpha_primal), float(alpha_dual), int(which),
                                               self._blocks(out)), "hb_iterate_take_step")
 
+    def adjust_duals_plh(self, it: dict, mu: float, kappa_sigma: float):
+        """hiopIterate::adjustDuals_primalLogHessian: clamps zl, zu, vl, vu of `it` in place."""
+        check(self.ctx.L.hb_iterate_adjust_duals_plh(self.h, self._blocks(it), float(mu), float(kappa_sigma)), "hb_iterate_adjust_duals_plh")
+
     def logbar(self, it: dict, f: float, mu: float, kappa_d: float, grad_f=None, grad_x=None, grad_d=None) -> float:
         fl = ctypes.c_double(0.0)
         check(self.ctx.L.hb_iterate_logbar(self.h, self._blocks(it), float(f), float(mu), float(kappa_d), _ptr(grad_f), _ptr(grad_x), _ptr(grad_d),

@@ -209,11 +209,14 @@ int hb_lowrank_residual_update(hb_lowrank* k, const double* const* it, const dou
  *     with alpha_dual) (:366-390); out may alias it.
  *   hb_iterate_logbar: hiopLogBarProblem::updateWithNlpInfo (hiopLogBarProblem.hpp:83-120): f_logbar = f - mu sum log(slacks) +
  *     kappa_d mu sum (one-sided slacks), grad_x_logbar = grad_f - mu/sxl + mu/sxu + kappa_d mu (ixl - ixu), grad_d_logbar likewise;
- *     with both gradient pointers NULL it is updateWithNlpInfo_trial_funcOnly (:121-132, function value only). */
+ *     with both gradient pointers NULL it is updateWithNlpInfo_trial_funcOnly (:121-132, function value only).
+ *   hb_iterate_adjust_duals_plh: hiopIterate::adjustDuals_primalLogHessian (hiopIterate.cpp:508-521, hiopVectorPar.cpp:1117-1148):
+ *     zl, zu, vl, vu are clamped in place to [mu/(kappa_Sigma s), kappa_Sigma mu/s] on their patterns. */
 int hb_iterate_fraction_to_bdry(hb_lowrank* k, const double* const* it, const double* const* dir, double tau, double* alpha_primal,
                                 double* alpha_dual);
 int hb_iterate_take_step(hb_lowrank* k, const double* const* it, const double* const* dir, double alpha_primal, double alpha_dual, int which,
                          double* const* out);
+int hb_iterate_adjust_duals_plh(hb_lowrank* k, double* const* it, double mu, double kappa_sigma);
 int hb_iterate_logbar(hb_lowrank* k, const double* const* it, double f, double mu, double kappa_d, const double* grad_f, double* grad_x_logbar,
                       double* grad_d_logbar, double* f_logbar);
 /* LSQ multiplier (re)computation hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (src/Optimization/hiopDualsUpdater.cpp:

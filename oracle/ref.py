@@ -61,6 +61,8 @@ def lib():
         L.ref_qn_logbar_update.restype = ctypes.c_int
         L.ref_qn_fraction_to_bdry.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ctypes.c_double, dp, dp]
         L.ref_qn_fraction_to_bdry.restype = ctypes.c_int
+        L.ref_qn_adjust_duals.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.c_double, ctypes.c_double, ctypes.POINTER(dp)]
+        L.ref_qn_adjust_duals.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -261,6 +263,13 @@ class RefQn:
         lib().ref_qn_logbar_update(self.h, IA, ctypes.c_double(f), ctypes.c_double(mu), ctypes.c_double(kappa_d), g.ctypes.data_as(dp),
                                    gx.ctypes.data_as(dp), gd.ctypes.data_as(dp), fl.ctypes.data_as(dp))
         return float(fl[0]), gx, gd[:self.mineq].copy()
+
+    def adjust_duals(self, itr: dict, mu, kappa):
+        keep, IA = self._blocks(itr)
+        outs = [np.zeros(max(self.n, 1)), np.zeros(max(self.n, 1)), np.zeros(max(self.mineq, 1)), np.zeros(max(self.mineq, 1))]
+        OA = (dp * 4)(*[a.ctypes.data_as(dp) for a in outs])
+        lib().ref_qn_adjust_duals(self.h, IA, ctypes.c_double(mu), ctypes.c_double(kappa), OA)
+        return outs[0][:self.n].copy(), outs[1][:self.n].copy(), outs[2][:self.mineq].copy(), outs[3][:self.mineq].copy()
 
     def fraction_to_bdry(self, itr: dict, direction: dict, tau):
         k1, IA = self._blocks(itr)

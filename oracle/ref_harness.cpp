@@ -377,6 +377,16 @@ int ref_qn_logbar_update(void* h, const double* const* iter, double f, double mu
   return 0;
 }
 
+/// hiopIterate::adjustDuals_primalLogHessian (hiopIterate.cpp:508-521): zl, zu, vl, vu clamped in place, returned through out[0..3].
+int ref_qn_adjust_duals(void* h, const double* const* iter, double mu, double kappa, double* const* out)
+{
+  QnCtx* c = (QnCtx*)h;
+  plant_iterate(*c->it, iter);
+  c->it->adjustDuals_primalLogHessian(mu, kappa);
+  get_vec(c->it->zl, out[0]); get_vec(c->it->zu, out[1]); get_vec(c->it->vl, out[2]); get_vec(c->it->vu, out[3]);
+  return 0;
+}
+
 /// hiopIterate::fractionToTheBdry (hiopIterate.cpp:326-363): largest primal / dual step lengths keeping slacks and duals positive.
 int ref_qn_fraction_to_bdry(void* h, const double* const* iter, const double* const* dir, double tau, double* alpha_primal, double* alpha_dual)
 {

@@ -48,4 +48,13 @@ def test_line_search_pipeline_against_oracle(ctx, n, m, mz, mu, kd):
     np.testing.assert_array_equal(gx.cpu().numpy(), gxo)
     np.testing.assert_array_equal(gd.cpu().numpy(), gdo)
     assert k.logbar(it_d, 3.25, mu, kd) == fl
+    # adjustDuals_primalLogHessian: every branch of the clamp (duals spread over 12 decades), in place, bit for bit
+    itr2 = dict(itr)
+    for zk in ("zl", "zu", "vl", "vu"):
+        itr2[zk] = itr[zk] * 10.0 ** rng.integers(-6, 7, size=np.asarray(itr[zk]).size)
+    it2_d = {kk: D(np.ascontiguousarray(v)) for kk, v in itr2.items()}
+    k.adjust_duals_plh(it2_d, mu, 50.0)
+    ctx.sync()
+    for name, want in zip(("zl", "zu", "vl", "vu"), ko.iterate_adjust_duals(itr2, pat, mu, 50.0)):
+        np.testing.assert_array_equal(it2_d[name].cpu().numpy(), want, err_msg=name)
     k.close()

@@ -239,6 +239,14 @@ def test_logbar_and_fraction_to_bdry_match_reference(n, m, mz, mu, kd):
     np.testing.assert_array_equal(gd, gd_r)
     rng = np.random.default_rng(12)
     direction = {k: rng.standard_normal(np.asarray(v).size) * np.where(np.asarray(v) != 0, 1.0, 0.0) for k, v in itr.items()}
+    # adjustDuals_primalLogHessian: duals scattered over several decades so that every branch of the clamp is taken
+    itr2 = dict(itr)
+    for zk in ("zl", "zu", "vl", "vu"):
+        itr2[zk] = itr[zk] * 10.0 ** rng.integers(-6, 7, size=np.asarray(itr[zk]).size)
+    got = ko.iterate_adjust_duals(itr2, pat, mu, 1e10 if kd == 0.0 else 50.0)
+    want = q.adjust_duals(itr2, mu, 1e10 if kd == 0.0 else 50.0)
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
     ap_r, ad_r = q.fraction_to_bdry(itr, direction, 0.995)
     ap, ad = ko.iterate_fraction_to_bdry(itr, direction, 0.995, pat)
     assert ap == ap_r and ad == ad_r, ((ap, ad), (ap_r, ad_r))
