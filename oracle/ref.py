@@ -63,6 +63,9 @@ def lib():
         L.ref_qn_fraction_to_bdry.restype = ctypes.c_int
         L.ref_qn_adjust_duals.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.c_double, ctypes.c_double, ctypes.POINTER(dp)]
         L.ref_qn_adjust_duals.restype = ctypes.c_int
+        L.ref_qn_adjust_small_slacks.argtypes = [ctypes.c_void_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ctypes.c_double, dp, dp, dp, dp,
+                                                 ctypes.POINTER(dp)]
+        L.ref_qn_adjust_small_slacks.restype = ctypes.c_int
         L.ref_bicgstab_dense.argtypes = [ctypes.c_int, dp, dp, dp, ctypes.c_double, ctypes.c_int, dp]
         L.ref_bicgstab_dense.restype = ctypes.c_int
         L.ref_symdense_factor_solve.argtypes = [ctypes.c_int, dp, ctypes.c_int, dp, dp, dp]
@@ -270,6 +273,15 @@ class RefQn:
         OA = (dp * 4)(*[a.ctypes.data_as(dp) for a in outs])
         lib().ref_qn_adjust_duals(self.h, IA, ctypes.c_double(mu), ctypes.c_double(kappa), OA)
         return outs[0][:self.n].copy(), outs[1][:self.n].copy(), outs[2][:self.mineq].copy(), outs[3][:self.mineq].copy()
+
+    def adjust_small_slacks(self, itr: dict, itr_curr: dict, mu, xl, xu, dl, du):
+        k1, IA = self._blocks(itr)
+        k2, CA = self._blocks(itr_curr)
+        b = [np.ascontiguousarray(v if np.asarray(v).size else np.zeros(1), dtype=np.float64) for v in (xl, xu, dl, du)]
+        outs = [np.zeros(max(self.n, 1)), np.zeros(max(self.n, 1)), np.zeros(max(self.mineq, 1)), np.zeros(max(self.mineq, 1))]
+        OA = (dp * 4)(*[a.ctypes.data_as(dp) for a in outs])
+        num = lib().ref_qn_adjust_small_slacks(self.h, IA, CA, ctypes.c_double(mu), *[v.ctypes.data_as(dp) for v in b], OA)
+        return num, (outs[0][:self.n].copy(), outs[1][:self.n].copy(), outs[2][:self.mineq].copy(), outs[3][:self.mineq].copy())
 
     def fraction_to_bdry(self, itr: dict, direction: dict, tau):
         k1, IA = self._blocks(itr)

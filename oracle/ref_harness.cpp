@@ -387,6 +387,21 @@ int ref_qn_adjust_duals(void* h, const double* const* iter, double mu, double ka
   return 0;
 }
 
+/// hiopIterate::adjust_small_slacks (hiopIterate.cpp:481-505) on the slacks of `iter` with the duals of `iter_curr`, bounds as given.
+/// out[0..3] = sxl, sxu, sdl, sdu afterwards; returns the number of adjusted slacks.
+int ref_qn_adjust_small_slacks(void* h, const double* const* iter, const double* const* iter_curr, double mu, const double* xl, const double* xu,
+                               const double* dl, const double* du, double* const* out)
+{
+  QnCtx* c = (QnCtx*)h;
+  plant_iterate(*c->it, iter);
+  hiopIterate cur(c->nlp);
+  plant_iterate(cur, iter_curr);
+  set_vec(c->nlp->xl_, xl); set_vec(c->nlp->xu_, xu); set_vec(c->nlp->dl_, dl); set_vec(c->nlp->du_, du);
+  const int n = c->it->adjust_small_slacks(cur, mu);
+  get_vec(c->it->sxl, out[0]); get_vec(c->it->sxu, out[1]); get_vec(c->it->sdl, out[2]); get_vec(c->it->sdu, out[3]);
+  return n;
+}
+
 /// hiopIterate::fractionToTheBdry (hiopIterate.cpp:326-363): largest primal / dual step lengths keeping slacks and duals positive.
 int ref_qn_fraction_to_bdry(void* h, const double* const* iter, const double* const* dir, double tau, double* alpha_primal, double* alpha_dual)
 {

@@ -253,6 +253,32 @@ def test_logbar_and_fraction_to_bdry_match_reference(n, m, mz, mu, kd):
     q.close()
 
 
+@pytest.mark.parametrize("mu", [1e-2, 10.0])
+def test_adjust_small_slacks_matches_reference(mu):
+    """hiopIterate::adjust_small_slacks: slacks that collapsed to (or below) zero are pushed back; untouched when none is small."""
+    p = synth.make_qn_problem(600, 12, 0, masked_zero_divisors=True)
+    itr, dat = synth.make_iterate(p)
+    pat = dict(ixl=p.ixl, ixu=p.ixu, idl=p.idl, idu=p.idu)
+    rng = np.random.default_rng(4)
+    q = _ref_system(p)
+    for collapse in (True, False):
+        trial = {k: np.array(v, dtype=np.float64) for k, v in itr.items()}
+        for s_, ptn in (("sxl", "ixl"), ("sxu", "ixu"), ("sdl", "idl"), ("sdu", "idu")):
+            trial[s_] = np.where(pat[ptn] == 1.0, np.abs(trial[s_]) + 1e-3, 0.0)
+            if collapse:
+                hit = (rng.random(trial[s_].size) < 0.2) & (pat[ptn] == 1.0)
+                trial[s_] = np.where(hit, rng.choice([0.0, -1e-9, 1e-20, 3e-17], size=trial[s_].size), trial[s_])
+        num_r, got_r = q.adjust_small_slacks(trial, itr, mu, dat["xl"], dat["xu"], dat["dl"], dat["du"])
+        num = 0
+        for (s_, ptn, bnd, dual), want in zip((("sxl", "ixl", "xl", "zl"), ("sxu", "ixu", "xu", "zu"), ("sdl", "idl", "dl", "vl"),
+                                                ("sdu", "idu", "du", "vu")), got_r):
+            new, k = ko.adjust_small_slack(trial[s_], dat[bnd], itr[dual], pat[ptn], mu)
+            num += k
+            np.testing.assert_array_equal(new, want, err_msg=s_)
+        assert num == num_r and (num > 0) == collapse
+    q.close()
+
+
 def test_hess_times_vec_matches_reference():
     p = synth.make_qn_problem(900, 3, 5)
     q = _ref_system(p)
