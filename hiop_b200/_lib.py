@@ -125,6 +125,7 @@ def lib() -> ctypes.CDLL:
     f("hb_iterate_fraction_to_bdry", c_i, c_vp, P(c_vp), P(c_vp), c_d, P(c_d), P(c_d))
     f("hb_iterate_take_step", c_i, c_vp, P(c_vp), P(c_vp), c_d, c_d, c_i, P(c_vp))
     f("hb_iterate_adjust_duals_plh", c_i, c_vp, P(c_vp), c_d, c_d)
+    f("hb_iterate_adjust_small_slacks", c_i, c_vp, P(c_vp), P(c_vp), c_d, c_dp, c_dp, c_dp, c_dp, P(c_i))
     f("hb_iterate_logbar", c_i, c_vp, P(c_vp), c_d, c_d, c_d, c_dp, c_dp, c_dp, P(c_d))
     f("hb_lowrank_lsq_duals", c_i, c_vp, *([c_dp] * 7))
     f("hb_lowrank_secant_reset", c_i, c_vp, c_d, c_i)

@@ -146,6 +146,40 @@ k_adjust_duals(long long n, double mu, double kappa, const double* __restrict__ 
   }
 }
 
+// hiopIterate::adjust_small_slacks for one slack block (hiopIterate.cpp:413-479), the reference's chain of ~20 vector calls per element,
+// same operations in the same order (bit-identical); cnt counts the entries whose shifted slack was negative (numOfElemsLessThan).
+__global__ void __launch_bounds__(ET)
+k_adjust_small_slack(long long n, double mu, double small_val, double scale_fact, const double* __restrict__ bound, const double* __restrict__ dual,
+                     const double* __restrict__ sel, double* __restrict__ slack, int* __restrict__ cnt)
+{
+  int local = 0;
+  const long long stride = (long long)gridDim.x * ET;
+  for(long long i = (long long)blockIdx.x * ET + threadIdx.x; i < n; i += stride) {
+    const double s = slack[i];
+    const bool on = sel[i] == 1.0;
+    double a1 = s;
+    if(on) a1 = __dadd_rn(a1, -small_val);
+    if(a1 > 0.0) a1 = 0.0;
+    if(a1 < 0.0) local++;
+    a1 = __dmul_rn((double)((0.0 < a1) - (a1 < 0.0)), -1.0);
+    const double s0 = s < 0.0 ? 0.0 : s;
+    double a2 = on ? __ddiv_rn(mu, dual[i]) : 0.0;
+    const double a3 = on ? small_val : 0.0;
+    if(a2 < a3) a2 = a3;
+    a2 = __dadd_rn(a2, __dmul_rn(-1.0, s0));
+    a1 = __dmul_rn(a1, a2);
+    a1 = __dadd_rn(a1, __dmul_rn(1.0, s0));
+    double b2 = on ? 1.0 : 0.0;
+    const double b3 = fabs(bound[i]);
+    if(b2 < b3) b2 = b3;
+    b2 = __dmul_rn(b2, scale_fact);
+    b2 = __dadd_rn(b2, __dmul_rn(1.0, s0));
+    if(a1 > b2) a1 = b2;
+    slack[i] = a1;
+  }
+  if(local) atomicAdd(cnt, local);
+}
+
 inline int grid_for(hb_ctx* c, long long n)
 {
   long long g = (n + ET - 1) / ET;
@@ -236,6 +270,36 @@ extern "C" int hb_iterate_adjust_duals_plh(hb_lowrank* k, double* const* it, dou
     k_adjust_duals<<<grid_for(c, k->mineq), ET, 0, c->stream>>>(k->mineq, mu, kappa_sigma, it[SDL], it[SDU], k->idl, k->idu, it[VL], it[VU]);
     HB_LAUNCHED();
   }
+  return HB_OK;
+}
+
+extern "C" int hb_iterate_adjust_small_slacks(hb_lowrank* k, double* const* it, const double* const* it_curr, double mu, const double* xl,
+                                              const double* xu, const double* dl, const double* du, int* num_adjusted)
+{
+  HB_REQUIRE(k && it && it_curr, "hb_iterate_adjust_small_slacks: null argument");
+  HB_REQUIRE(k->n == 0 || k->ixl, "hb_iterate_adjust_small_slacks: patterns not set");
+  hb_ctx* c = k->ctx;
+  const double eps = 2.220446049250313e-16;
+  const double small_val = eps * fmin(1.0, mu);
+  const double scale_fact = pow(eps, 0.75);
+  HB_CHECK(hb_ws_reserve(c, 64));
+  int* cnt = (int*)c->ws;
+  HB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), c->stream));
+  struct Blk { int s, z; const double* bound; const double* sel; long long len; };
+  const Blk blks[4] = {{SXL, ZL, xl, k->ixl, k->n}, {SXU, ZU, xu, k->ixu, k->n}, {SDL, VL, dl, k->idl, (long long)k->mineq},
+                       {SDU, VU, du, k->idu, (long long)k->mineq}};
+  for(const Blk& b : blks) {
+    if(b.len == 0) continue;
+    double smin = 0.0;
+    HB_CHECK(hb_vec_min_w_pattern(c, b.len, it[b.s], b.sel, &smin)); // slack.min_w_pattern(select) :432
+    if(!(smin < small_val)) continue;
+    k_adjust_small_slack<<<grid_for(c, b.len), ET, 0, c->stream>>>(b.len, mu, small_val, scale_fact, b.bound, it_curr[b.z], b.sel, it[b.s], cnt);
+    HB_LAUNCHED();
+  }
+  int h = 0;
+  HB_CUDA(cudaMemcpyAsync(&h, cnt, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  if(num_adjusted) *num_adjusted = h;
   return HB_OK;
 }
 

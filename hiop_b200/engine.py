@@ -294,6 +294,13 @@ class KKTLinSysLowRank:
         """hiopIterate::adjustDuals_primalLogHessian: clamps zl, zu, vl, vu of `it` in place."""
         check(self.ctx.L.hb_iterate_adjust_duals_plh(self.h, self._blocks(it), float(mu), float(kappa_sigma)), "hb_iterate_adjust_duals_plh")
 
+    def adjust_small_slacks(self, it: dict, it_curr: dict, mu: float, xl, xu, dl, du) -> int:
+        """hiopIterate::adjust_small_slacks: fixes the slacks of `it` in place; returns how many were adjusted."""
+        num = ctypes.c_int(0)
+        check(self.ctx.L.hb_iterate_adjust_small_slacks(self.h, self._blocks(it), self._blocks(it_curr), float(mu), _ptr(xl), _ptr(xu), _ptr(dl),
+                                                        _ptr(du), ctypes.byref(num)), "hb_iterate_adjust_small_slacks")
+        return num.value
+
     def logbar(self, it: dict, f: float, mu: float, kappa_d: float, grad_f=None, grad_x=None, grad_d=None) -> float:
         fl = ctypes.c_double(0.0)
         check(self.ctx.L.hb_iterate_logbar(self.h, self._blocks(it), float(f), float(mu), float(kappa_d), _ptr(grad_f), _ptr(grad_x), _ptr(grad_d),

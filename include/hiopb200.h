@@ -217,6 +217,11 @@ int hb_iterate_fraction_to_bdry(hb_lowrank* k, const double* const* it, const do
 int hb_iterate_take_step(hb_lowrank* k, const double* const* it, const double* const* dir, double alpha_primal, double alpha_dual, int which,
                          double* const* out);
 int hb_iterate_adjust_duals_plh(hb_lowrank* k, double* const* it, double mu, double kappa_sigma);
+/* hiopIterate::adjust_small_slacks (hiopIterate.cpp:413-505): slacks of `it` that fell below eps*min(1,mu) on their pattern are pushed back
+ * (in place) using the bound duals of it_curr and the bounds xl, xu (n_local), dl, du (m_ineq); *num_adjusted = number of adjusted
+ * entries on this rank. A block whose smallest slack is not small is left untouched, like in the reference. */
+int hb_iterate_adjust_small_slacks(hb_lowrank* k, double* const* it, const double* const* it_curr, double mu, const double* xl, const double* xu,
+                                   const double* dl, const double* du, int* num_adjusted);
 int hb_iterate_logbar(hb_lowrank* k, const double* const* it, double f, double mu, double kappa_d, const double* grad_f, double* grad_x_logbar,
                       double* grad_d_logbar, double* f_logbar);
 /* LSQ multiplier (re)computation hiopDualsLsqUpdateLinsysRedDenseSymPD::do_lsq_update (src/Optimization/hiopDualsUpdater.cpp:

@@ -58,3 +58,35 @@ def test_line_search_pipeline_against_oracle(ctx, n, m, mz, mu, kd):
     for name, want in zip(("zl", "zu", "vl", "vu"), ko.iterate_adjust_duals(itr2, pat, mu, 50.0)):
         np.testing.assert_array_equal(it2_d[name].cpu().numpy(), want, err_msg=name)
     k.close()
+
+
+@pytest.mark.parametrize("mu", [1e-2, 10.0])
+def test_adjust_small_slacks_against_oracle(ctx, mu):
+    """hiopIterate::adjust_small_slacks: collapsed slacks are pushed back exactly like the reference's chain of vector operations does
+    (oracle pinned bit-for-bit in tests/test_oracle_vs_ref.py); blocks without a small slack stay untouched."""
+    P = synth.make_qn_problem(5000, 24, 0, masked_zero_divisors=True, seed=3)
+    p = _as_dict(P)
+    itr, dat = synth.make_iterate(P)
+    pat = dict(ixl=P.ixl, ixu=P.ixu, idl=P.idl, idu=P.idu)
+    rng = np.random.default_rng(4)
+    k, T = _setup_kkt(ctx, p)
+    D = ctx.to_device
+    cur_d = {kk: D(np.ascontiguousarray(v)) for kk, v in itr.items()}
+    bounds = [D(dat[b]) for b in ("xl", "xu", "dl", "du")]
+    for collapse in (True, False):
+        trial = {kk: np.array(v, dtype=np.float64) for kk, v in itr.items()}
+        for s_, ptn in (("sxl", "ixl"), ("sxu", "ixu"), ("sdl", "idl"), ("sdu", "idu")):
+            trial[s_] = np.where(pat[ptn] == 1.0, np.abs(trial[s_]) + 1e-3, 0.0)
+            if collapse:
+                hit = (rng.random(trial[s_].size) < 0.2) & (pat[ptn] == 1.0)
+                trial[s_] = np.where(hit, rng.choice([0.0, -1e-9, 1e-20, 3e-17], size=trial[s_].size), trial[s_])
+        tr_d = {kk: D(np.ascontiguousarray(v)) for kk, v in trial.items()}
+        num = k.adjust_small_slacks(tr_d, cur_d, mu, *bounds)
+        ctx.sync()
+        want_num = 0
+        for s_, ptn, bnd, dual in (("sxl", "ixl", "xl", "zl"), ("sxu", "ixu", "xu", "zu"), ("sdl", "idl", "dl", "vl"), ("sdu", "idu", "du", "vu")):
+            new, cnt = ko.adjust_small_slack(trial[s_], dat[bnd], itr[dual], pat[ptn], mu)
+            want_num += cnt
+            np.testing.assert_array_equal(tr_d[s_].cpu().numpy(), new, err_msg=s_)
+        assert num == want_num and (num > 0) == collapse
+    k.close()
