@@ -21,3 +21,19 @@ def reductions_per_system(m: int, l: int) -> list[tuple[str, int]]:
         ("J dx_tmp (hiopMatrixDenseRowMajor.cpp:487, beta applied on rank 0 only :464-467)", m),
         ("second hiopHessianLowRank::solve", 2 * l),
     ]
+
+
+# compound (12-block) vectors of the outer refinement: which blocks are sharded along n and which are replicated on every rank
+N_BLOCKS = ("x", "sxl", "sxu", "zl", "zu")
+M_BLOCKS = ("d", "yc", "yd", "sdl", "sdu", "vl", "vu")
+
+
+def compound_reduction_contribution(rank: int, blocks: dict, op):
+    """What one rank feeds into the single all-reduce of a compound-vector reduction (dot, squared 2-norm, ...): its shard of the
+    n-sized blocks always, the replicated m-sized blocks only on rank 0 -- the rule hb_krylov.cu implements by shortening the
+    reduction length on ranks != 0 (hiopVectorCompoundPD reduces each block in its own communicator instead,
+    src/LinAlg/hiopVectorCompoundPD.cpp:438-461). `op(block_name, array) -> float` is the local reduction of one block."""
+    total = sum(op(k, blocks[k]) for k in N_BLOCKS)
+    if rank == 0:
+        total += sum(op(k, blocks[k]) for k in M_BLOCKS)
+    return total

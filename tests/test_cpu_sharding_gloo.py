@@ -77,6 +77,52 @@ def test_column_sharded_kkt_matches_single_rank(n, m, l):
     assert np.abs(dxs - dx).max() <= 1e-9 * np.abs(dx).max()
 
 
+def _worker_compound(rank, world, port, n, mi, me, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(5)
+    sizes = dict(x=n, d=mi, yc=me, yd=mi, sxl=n, sxu=n, sdl=mi, sdu=mi, zl=n, zu=n, vl=mi, vu=mi)
+    a = {k: rng.standard_normal(v) for k, v in sizes.items()}
+    b = {k: rng.standard_normal(v) for k, v in sizes.items()}
+    lo, hi = sharding.column_range(n, world, rank)
+    shard = lambda d: {k: (v[lo:hi] if k in sharding.N_BLOCKS else v) for k, v in d.items()}
+    sa, sb = shard(a), shard(b)
+    # dot product and 2-norm of BiCGStab: one SUM all-reduce each
+    dot = _allreduce(np.array([sharding.compound_reduction_contribution(rank, sa, lambda k, v: float(v @ sb[k]))]))[0]
+    nrm2 = np.sqrt(_allreduce(np.array([sharding.compound_reduction_contribution(rank, sa, lambda k, v: float(v @ v))]))[0])
+    # inf-norms of the residual (hiopResidual.cpp:349-365): MAX all-reduce of the sharded blocks, replicated blocks combined locally
+    t = torch.tensor([max(np.abs(sa[k]).max() for k in sharding.N_BLOCKS)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    inf = max(float(t[0]), max(np.abs(sa[k]).max(initial=0.0) for k in sharding.M_BLOCKS))
+    # fraction-to-the-boundary (hiopIterate.cpp:356-360): MIN all-reduce
+    tau = 0.995
+    ftb = lambda x, dx: float(np.min(np.where(dx < 0, np.minimum(1.0, -tau * np.abs(x) / np.where(dx < 0, dx, -1.0)), 1.0), initial=1.0))
+    t = torch.tensor([min(ftb(sa[k], sb[k]) for k in ("sxl", "sxu"))], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    alpha = min(float(t[0]), min(ftb(sa[k], sb[k]) for k in ("sdl", "sdu")))
+    out[rank] = (dot, nrm2, inf, alpha)
+    if rank == 0:
+        fa, fb = np.concatenate([a[k] for k in sizes]), np.concatenate([b[k] for k in sizes])
+        out["want"] = (float(fa @ fb), float(np.linalg.norm(fa)), float(np.abs(fa).max()),
+                       min(ftb(a[k], b[k]) for k in ("sxl", "sxu", "sdl", "sdu")))
+    dist.destroy_process_group()
+
+
+def test_compound_vector_reductions_count_replicated_blocks_once():
+    """The reduction rules of the sharded BiCGStab / residual norms / step-length search: every rank ends with the value a single
+    rank would compute on the unsharded 12-block vector."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = 29500 + (os.getpid() + 77) % 2000
+    mp.spawn(_worker_compound, args=(2, port, 1001, 7, 5, out), nprocs=2, join=True)
+    want = out["want"]
+    for rank in (0, 1):
+        got = out[rank]
+        assert abs(got[0] - want[0]) <= 1e-12 * max(1.0, abs(want[0]))
+        assert abs(got[1] - want[1]) <= 1e-12 * want[1]
+        assert got[2] == want[2] and got[3] == want[3]
+
+
 def test_column_range_partitions_exactly():
     for n in (0, 1, 7, 1000003):
         for w in (1, 2, 3, 8):
