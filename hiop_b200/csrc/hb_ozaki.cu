@@ -542,6 +542,9 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
   HB_CHECK(hb_ws_reserve(c, sizeof(double) * (size_t)st.n_items * TM * TN));
   // (t+1) * Kc * 2^12 < 2^31 with t+1 <= S  ->  Kc <= 2^19 / S columns
   int chunk_stages = (int)((524288 / S) / KS);
+  // strict: S products of |q q'| <= 2^12 per column must stay BELOW 2^31 (S = 8 gives exactly 2^31 with 512 stages of 128 columns when
+  // every digit is -64, see tests/test_cpu_oz_model.py)
+  while((long long)S * chunk_stages * KS * 4096 >= (1LL << 31)) chunk_stages--;
   if(c->timing) HB_CUDA(cudaEventRecord(c->ev_syrk0, c->stream));
   if(S == 6) HB_CHECK(launch_gemm<6>(c, st, chunk_stages, (double*)c->ws));
   else if(S == 7) HB_CHECK(launch_gemm<7>(c, st, chunk_stages, (double*)c->ws));
