@@ -451,6 +451,20 @@ def run_engine(args):
                                    "2 x its bf16_tflops = 3403 is below what this kernel executes, so it is not usable as a ceiling)",
                     "note": "achieved/peak count int8 operations (2 per MAC); the FP64 work the kernel stands in for is fp64_equivalent_flops",
                     "fp64_equivalent_flops": fl, "fp64_equivalent_tflops_gemm_only": fl / (syrk * 1e-3) / 1e12}
+    if mode == 8 and n_local == N_FULL and m == M_FULL and l == L_MEM:
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this workload, from the committed ncu --set full capture
+        try:
+            unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+            tot = 0.0
+            for row in open(os.path.join(ROOT, "profiles", "ozgemm_r01_ncu_full.csv")):
+                parts = [q.strip().strip('"') for q in row.strip().split(",")]
+                if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                    tot += float(parts[2]) * unit[parts[1]]
+            if tot > 0:
+                roofline["traffic"] = tot
+                roofline["traffic_source"] = "profiles/ozgemm_r01_ncu_full.csv (ncu --set full, one launch; algorithmic operand bytes: 8 slices x 1012 x 1e6 = 8.1e9)"
+        except Exception:
+            pass
     roofline["hbm_algorithmic_GBs_whole_step"] = algorithmic_bytes(n_local, m, l) / (ms_step * 1e-3) / 1e9
     roofline["condense_mode"] = "fp64_dmma" if mode == 0 else f"int8_slices_{mode}"
     line = {"metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
