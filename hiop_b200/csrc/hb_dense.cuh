@@ -22,3 +22,25 @@ int hb_dense_chol_with_inverses(hb_ctx* c, int N, double* A, int lda, int* info_
 int hb_dense_spd_solve_refine2(hb_ctx* c, int N, const double* F, int ldf, const double* invd /* NULL: one-CTA solve */, const double* s,
                                const double* Nref, int ldn, const double* rhs, double* x, double* work2N2, double tol, int max_refine,
                                double* stats_dev);
+
+// ---- large-N path (hb_dense_big.cu): blocked Cholesky / no-pivot LDL^T with look-ahead, 128 x 128 diagonal-block inverses, blocked solves ----
+struct hb_big
+{
+  cudaStream_t panel_stream = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_upd = nullptr;
+  double* InvAll = nullptr;         // ceil(N/128) inverses of the 128 x 128 diagonal triangles of the factor (column-major, zeros above)
+  double* W[2] = {nullptr, nullptr}; // LDL^T: W = L*D of the current panel (double-buffered across the look-ahead)
+  double* dinv = nullptr;
+  double* partial = nullptr;        // solve: per-CTA partial products
+  int* counter = nullptr;           // solve: ticket of the "last CTA finishes the step" pattern (self-resetting)
+  double* xtmp = nullptr;           // permuted rhs (Bunch-Kaufman)
+  int capN = 0;
+  bool inv_valid = false;
+};
+int hb_big_init(hb_ctx* c, hb_big* b);
+void hb_big_release(hb_big* b);
+int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w);
+int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ldl, int* info_dev);
+int hb_big_trailing_from_state(hb_ctx* c, int N, double* A, long long lda, const double* W, long long ldw, const int* state_dev, int r0_min, cudaStream_t st);
+int hb_big_block_inverses(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, bool unit);
+int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const int* perm_dev, double* x);

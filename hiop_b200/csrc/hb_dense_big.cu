@@ -1,0 +1,902 @@
+// Large-N dense symmetric factorizations and solves (the B1 plug-in at MDS / sweep sizes, N up to a few 10^4).
+//
+// Roles: hiopLinSolverSymDenseLapack::matrixChanged / solve (src/LinAlg/hiopLinSolverSymDenseLapack.hpp:75-192) and the MAGMA twins
+// magma_dsytrf_nopiv_gpu / magma_dpotrf (src/LinAlg/hiopLinSolverSymDenseMagma.cpp:349, 455) + their triangular solves (:250, :420).
+//
+// Storage convention as in hb_dense.cu: N x N row-major with the UPPER triangle valid = column-major LOWER, Lc(i,j) = A[j*lda + i].
+//
+// Factorization (Cholesky LL^T and no-pivot LDL^T), block size 128, right-looking with one block of look-ahead on two streams:
+//   panel stream  : k_diag128   one CTA factors the 128 x 128 diagonal block in shared memory (16-wide sub-panels) and also emits the
+//                               INVERSE of its triangular factor (kept: the solves use it),
+//                   k_gemm_pq<128,STORE>   L21 = A21 * L11^-T as a DMMA GEMM against that inverse (LDL^T: W21 = A21 L11^-T, L21 = W21 D^-1)
+//   update stream : k_gemm_pq<64,SUB>      A22 -= W21 * L21^T on 128 x 64 tiles of the lower triangle: first the 128 columns of the next
+//                                          panel (the panel stream continues as soon as these are done), then the rest.
+//   k_gemm_pq: operands are "p-major" (P[p][i], i contiguous = a column of the factor), 16 x tile chunks through a 4-stage cp.async ring,
+//   mma.sync.m8n8k4.f64 (SASS DMMA), 8 warps, 2 CTAs per SM for the update tiles so that one tile's read-modify-write epilogue overlaps
+//   the other's MMA loop; the epilogue goes through shared memory so that the global accesses run down the (contiguous) columns.
+//
+// Solves (all three modes incl. Bunch-Kaufman in permuted form): one launch per 256 rows per sweep. Forward step (left-looking):
+// the CTAs compute partial products of block-row k against the already solved part, the LAST CTA to finish (ticket) adds them in a
+// fixed order and applies the stored 128 x 128 inverses -- deterministic, no atomics on the data. Backward step likewise with the
+// rows below. N = 8192: 2 x 32 launches.
+#include "hb_common.cuh"
+#include "hb_dense.cuh"
+#include <cstdlib>
+
+namespace {
+
+#define LC(A, lda, i, j) (A)[(size_t)(j) * (lda) + (i)]
+
+constexpr int BB = 128;  // factorization block = size of the stored diagonal-block inverses
+constexpr int KC = 16;   // operand rows per pipeline stage
+constexpr int GST = 4;   // pipeline stages
+constexpr int TM = 128;  // tile rows (i)
+constexpr int PLD = TM + 4;
+constexpr int CLD = TM + 2;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b)
+{
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes)
+{
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NW>
+__device__ __forceinline__ void cp_async_wait()
+{
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(NW));
+}
+
+enum { EPI_SUB = 0, EPI_STORE = 1, EPI_STORE_LDL = 2 };
+
+struct GemmArgs
+{
+  const double* P;   // P[p*ldp + i], absolute row index i
+  long long ldp;
+  const double* Q;   // Q[p*ldq + (j - qsub)]
+  long long ldq;
+  int qsub;
+  int kb;            // number of operand rows (K), <= 128
+  double* C;         // C[j*ldc + i]
+  long long ldc;
+  int i_base, j_base, i_end, j_end;
+  int tj0;           // first column tile of this launch
+  double* W2;        // EPI_STORE_LDL: W2[(j - j_base)*ldw2 + i] = acc
+  long long ldw2;
+  const double* dinv; // EPI_STORE_LDL: C = acc * dinv[j - j_base]
+  const int* state;   // pivoted panels: k0 = state[0], kb = state[1] read on the device (Q = C + k0*ldc, origin k0 + kb)
+};
+
+template <int TN>
+struct GemmCfg
+{
+  static constexpr int QLD = TN + 4;
+  static constexpr int STAGE_D = KC * PLD + KC * QLD;
+  static constexpr size_t SMEM = sizeof(double) * ((size_t)GST * STAGE_D > (size_t)TN * CLD ? (size_t)GST * STAGE_D : (size_t)TN * CLD);
+};
+
+template <int TN, int EPI>
+__global__ void __launch_bounds__(256, (TN == 64 ? 2 : 1)) k_gemm_pq(const GemmArgs g)
+{
+  extern __shared__ __align__(16) unsigned char gsm_raw[];
+  double* sm = reinterpret_cast<double*>(gsm_raw);
+  constexpr int QLD = GemmCfg<TN>::QLD;
+  constexpr int STAGE_D = GemmCfg<TN>::STAGE_D;
+  constexpr int NJ = TN / 16; // 8-wide n fragments per warp (2 warps along j)
+
+  int kb = g.kb, i_base = g.i_base, j_base = g.j_base;
+  int jmin = g.j_base;
+  const double* Q = g.Q;
+  if(g.state) {
+    const int k0 = g.state[0];
+    kb = g.state[1];
+    if(kb <= 0) return;
+    jmin = k0 + kb;
+    i_base = j_base = jmin & ~1; // tile origins stay even (16-byte accesses); the column below the origin is masked out
+    Q = g.C + (size_t)k0 * g.ldc;
+  }
+  const int i0 = i_base + TM * blockIdx.x;
+  const int j0 = j_base + TN * (g.tj0 + blockIdx.y);
+  if(i0 >= g.i_end || j0 >= g.j_end) return;
+  if(EPI == EPI_SUB && i0 + TM - 1 < j0) return; // tile entirely above the diagonal
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int nch = (kb + KC - 1) / KC;
+  const double* P = g.P;
+
+  auto load_chunk = [&](int ch) {
+    double* sP = sm + (size_t)(ch % GST) * STAGE_D;
+    double* sQ = sP + KC * PLD;
+#pragma unroll
+    for(int q = 0; q < (KC * TM / 2) / 256; q++) {
+      const int idx = tid + 256 * q;
+      const int p = idx >> 6, ic = idx & 63;
+      const int pp = ch * KC + p, i = i0 + 2 * ic;
+      const bool v = pp < kb && i < g.i_end;
+      cp_async16(&sP[p * PLD + 2 * ic], v ? P + (size_t)pp * g.ldp + i : P, v ? 16 : 0);
+    }
+#pragma unroll
+    for(int q = 0; q < (KC * TN / 2) / 256; q++) {
+      const int idx = tid + 256 * q;
+      const int p = idx / (TN / 2), jc = idx % (TN / 2);
+      const int pp = ch * KC + p, j = j0 + 2 * jc;
+      const bool v = pp < kb && j < g.j_end;
+      cp_async16(&sQ[p * QLD + 2 * jc], v ? Q + (size_t)pp * g.ldq + (j - g.qsub) : Q, v ? 16 : 0);
+    }
+  };
+
+  double acc[4][NJ][2];
+#pragma unroll
+  for(int a = 0; a < 4; a++)
+#pragma unroll
+    for(int b = 0; b < NJ; b++) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+#pragma unroll
+  for(int s = 0; s < GST - 1; s++) {
+    if(s < nch) load_chunk(s);
+    cp_async_commit();
+  }
+  for(int it = 0; it < nch; it++) {
+    cp_async_wait<GST - 2>();
+    __syncthreads();
+    {
+      const int nx = it + GST - 1;
+      if(nx < nch) load_chunk(nx);
+      cp_async_commit();
+    }
+    const double* sP = sm + (size_t)(it % GST) * STAGE_D;
+    const double* sQ = sP + KC * PLD;
+#pragma unroll
+    for(int kk = 0; kk < KC / 4; kk++) {
+      double af[4], bf[NJ];
+#pragma unroll
+      for(int a = 0; a < 4; a++) af[a] = sP[(kk * 4 + t4) * PLD + wm * 32 + a * 8 + gq];
+#pragma unroll
+      for(int b = 0; b < NJ; b++) bf[b] = sQ[(kk * 4 + t4) * QLD + wn * (TN / 2) + b * 8 + gq];
+#pragma unroll
+      for(int a = 0; a < 4; a++)
+#pragma unroll
+        for(int b = 0; b < NJ; b++) dmma884(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  // ---- epilogue: accumulators -> shared (column-major tile, stride CLD) -> global, running down the columns ----
+  double* sC = sm;
+#pragma unroll
+  for(int a = 0; a < 4; a++)
+#pragma unroll
+    for(int b = 0; b < NJ; b++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) sC[(wn * (TN / 2) + b * 8 + t4 * 2 + h) * CLD + wm * 32 + a * 8 + gq] = acc[a][b][h];
+  __syncthreads();
+  constexpr int ITEMS = TM * TN / 2 / 256; // double2 items per thread
+  constexpr int BATCH = 8;
+#pragma unroll 1
+  for(int b0 = 0; b0 < ITEMS; b0 += BATCH) {
+    double2 cur[BATCH];
+    if(EPI == EPI_SUB) {
+#pragma unroll
+      for(int s = 0; s < BATCH; s++) {
+        const int e = tid + (b0 + s) * 256;
+        const int jl = e >> 6, il = (e & 63) * 2;
+        const int gi = i0 + il, gj = j0 + jl;
+        cur[s] = make_double2(0.0, 0.0);
+        if(gj < g.j_end && gj >= jmin && gi + 1 >= gj && gi < g.i_end) {
+          if(gi >= gj && gi + 1 < g.i_end) cur[s] = *reinterpret_cast<const double2*>(&LC(g.C, g.ldc, gi, gj));
+          else {
+            if(gi >= gj) cur[s].x = LC(g.C, g.ldc, gi, gj);
+            if(gi + 1 < g.i_end) cur[s].y = LC(g.C, g.ldc, gi + 1, gj);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for(int s = 0; s < BATCH; s++) {
+      const int e = tid + (b0 + s) * 256;
+      const int jl = e >> 6, il = (e & 63) * 2;
+      const int gi = i0 + il, gj = j0 + jl;
+      if(gj >= g.j_end || gj < jmin || gi >= g.i_end) continue;
+      const double2 v = *reinterpret_cast<const double2*>(&sC[jl * CLD + il]);
+      if(EPI == EPI_SUB) {
+        if(gi + 1 < gj) continue;
+        if(gi >= gj && gi + 1 < g.i_end) *reinterpret_cast<double2*>(&LC(g.C, g.ldc, gi, gj)) = make_double2(cur[s].x - v.x, cur[s].y - v.y);
+        else {
+          if(gi >= gj) LC(g.C, g.ldc, gi, gj) = cur[s].x - v.x;
+          if(gi + 1 < g.i_end) LC(g.C, g.ldc, gi + 1, gj) = cur[s].y - v.y;
+        }
+      } else {
+        const bool two = gi + 1 < g.i_end;
+        double2 o = v;
+        if(EPI == EPI_STORE_LDL) {
+          const int c = gj - j_base;
+          if(two) *reinterpret_cast<double2*>(&g.W2[(size_t)c * g.ldw2 + gi]) = v;
+          else g.W2[(size_t)c * g.ldw2 + gi] = v.x;
+          const double r = g.dinv[c];
+          o.x *= r; o.y *= r;
+        }
+        if(two) *reinterpret_cast<double2*>(&LC(g.C, g.ldc, gi, gj)) = o;
+        else LC(g.C, g.ldc, gi, gj) = o.x;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// 128 x 128 diagonal block: factor (LL^T or LDL^T without pivoting) + inverse of the triangular factor, one CTA.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int DSB = BB + 1;
+constexpr int DTHREADS = 512;
+struct DiagSmem
+{
+  double D[BB * DSB];        // D[j*DSB + i] = element (i,j), i >= j; the slots i < j receive the strictly lower part of the inverse:
+                             // Inv(r,c), r > c, lives at D[r*DSB + c]
+  double Inv16[8 * 16 * 17]; // inverses of the eight 16 x 16 diagonal triangles
+  double Tt[112 * 17];
+  double idg[BB];            // diagonal of the inverse (1/L_rr; 1 for the unit factor of LDL^T)
+  double dv[BB];             // LDL^T: d_j
+  double rdv[BB];            // LDL^T: 1/d_j
+};
+
+template <bool LDL>
+__device__ void factor_block128(DiagSmem& S, int k0, int* info)
+{
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for(int kb = 0; kb < BB / 16; kb++) {
+    const int c0 = kb * 16;
+    if(warp == 0) {
+      double a[16];
+      double myr = 1.0;
+#pragma unroll
+      for(int c = 0; c < 16; c++) a[c] = (lane < 16 && c <= lane) ? S.D[(c0 + c) * DSB + c0 + lane] : 0.0;
+      // spelled out per column (a rolled 16 x 15 nest would put a[] in local memory)
+#define BIG_CHOL_COL(j)                                                                          \
+  {                                                                                              \
+    const double d = __shfl_sync(0xffffffffu, a[j], j);                                          \
+    if(!(d > 0.0) && lane == 0) atomicCAS(info, 0, k0 + c0 + j + 1);                             \
+    const double r = rsqrt(d);                                                                   \
+    if(lane == j) { a[j] = d * r; myr = r; }                                                     \
+    else if(lane > j) a[j] *= r;                                                                 \
+    _Pragma("unroll") for(int c = j + 1; c < 16; c++) {                                          \
+      const double lc = __shfl_sync(0xffffffffu, a[j], c);                                       \
+      if(lane >= c) a[c] -= a[j] * lc;                                                           \
+    }                                                                                            \
+  }
+#define BIG_LDL_COL(j)                                                                           \
+  {                                                                                              \
+    const double d = __shfl_sync(0xffffffffu, a[j], j);                                          \
+    if((d == 0.0 || d != d) && lane == 0) atomicCAS(info, 0, k0 + c0 + j + 1);                   \
+    const double r = 1.0 / d;                                                                    \
+    const double wj = a[j];                                                                      \
+    if(lane > j) a[j] = wj * r;                                                                  \
+    _Pragma("unroll") for(int c = j + 1; c < 16; c++) {                                          \
+      const double wc = __shfl_sync(0xffffffffu, wj, c);                                         \
+      if(lane >= c) a[c] -= a[j] * wc;                                                           \
+    }                                                                                            \
+  }
+      if(LDL) {
+        BIG_LDL_COL(0) BIG_LDL_COL(1) BIG_LDL_COL(2) BIG_LDL_COL(3) BIG_LDL_COL(4) BIG_LDL_COL(5) BIG_LDL_COL(6) BIG_LDL_COL(7)
+        BIG_LDL_COL(8) BIG_LDL_COL(9) BIG_LDL_COL(10) BIG_LDL_COL(11) BIG_LDL_COL(12) BIG_LDL_COL(13) BIG_LDL_COL(14) BIG_LDL_COL(15)
+      } else {
+        BIG_CHOL_COL(0) BIG_CHOL_COL(1) BIG_CHOL_COL(2) BIG_CHOL_COL(3) BIG_CHOL_COL(4) BIG_CHOL_COL(5) BIG_CHOL_COL(6) BIG_CHOL_COL(7)
+        BIG_CHOL_COL(8) BIG_CHOL_COL(9) BIG_CHOL_COL(10) BIG_CHOL_COL(11) BIG_CHOL_COL(12) BIG_CHOL_COL(13) BIG_CHOL_COL(14) BIG_CHOL_COL(15)
+      }
+#undef BIG_CHOL_COL
+#undef BIG_LDL_COL
+#pragma unroll
+      for(int c = 0; c < 16; c++)
+        if(lane < 16 && c <= lane) S.D[(c0 + c) * DSB + c0 + lane] = a[c];
+      if(lane < 16) {
+        S.idg[c0 + lane] = myr;
+        if(LDL) {
+          double dl = 0.0;
+#pragma unroll
+          for(int c = 0; c < 16; c++)
+            if(c == lane) dl = a[c];
+          S.dv[c0 + lane] = dl;
+          S.rdv[c0 + lane] = 1.0 / dl;
+        }
+      }
+      __syncwarp();
+      // column `lane` of X = T^-1 (T = the 16 x 16 triangle, unit diagonal for LDL^T), right-looking
+      {
+        double* inv = S.Inv16 + kb * 16 * 17;
+        double x[16], sacc[16];
+#pragma unroll
+        for(int r = 0; r < 16; r++) { x[r] = 0.0; sacc[r] = 0.0; }
+#pragma unroll
+        for(int q = 0; q < 16; q++) {
+          const double rq = __shfl_sync(0xffffffffu, myr, q);
+          if(q == lane) x[q] = rq;
+          else if(q > lane) x[q] = -sacc[q] * rq;
+#pragma unroll
+          for(int r = q + 1; r < 16; r++) sacc[r] += S.D[(c0 + q) * DSB + c0 + r] * x[q];
+        }
+        if(lane < 16) {
+#pragma unroll
+          for(int r = 0; r < 16; r++) {
+            inv[r * 17 + lane] = x[r];
+            if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r]; // strictly lower part of the inverse -> the unused upper slots
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int below = BB - c0 - 16;
+    {
+      const double* inv = S.Inv16 + kb * 16 * 17;
+      double y[4];
+#pragma unroll
+      for(int s = 0; s < 4; s++) {
+        const int e = tid + s * DTHREADS;
+        y[s] = 0.0;
+        if(e < below * 16) {
+          const int r = c0 + 16 + e % below, c = e / below;
+          double ac[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+          for(int q = 0; q < 16; q++)
+            if(q <= c) ac[q & 3] += S.D[(c0 + q) * DSB + r] * inv[c * 17 + q];
+          y[s] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
+          if(LDL) y[s] *= S.rdv[c0 + c];
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for(int s = 0; s < 4; s++) {
+        const int e = tid + s * DTHREADS;
+        if(e < below * 16) S.D[(c0 + e / below) * DSB + c0 + 16 + e % below] = y[s];
+      }
+    }
+    __syncthreads();
+    {
+      const int hb2 = below / 2;
+      for(int e = tid; e < hb2 * hb2; e += DTHREADS) {
+        const int tc = e / hb2, ti = e % hb2;
+        if(ti < tc) continue;
+        const int c = c0 + 16 + 2 * tc, i = c0 + 16 + 2 * ti;
+        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+#pragma unroll
+        for(int p = 0; p < 16; p++) {
+          const double li0 = S.D[(c0 + p) * DSB + i], li1 = S.D[(c0 + p) * DSB + i + 1];
+          double lc0 = S.D[(c0 + p) * DSB + c], lc1 = S.D[(c0 + p) * DSB + c + 1];
+          if(LDL) { const double dp = S.dv[c0 + p]; lc0 *= dp; lc1 *= dp; }
+          s00 += li0 * lc0; s10 += li1 * lc0; s01 += li0 * lc1; s11 += li1 * lc1;
+        }
+        S.D[c * DSB + i] -= s00;
+        S.D[c * DSB + i + 1] -= s10;
+        S.D[(c + 1) * DSB + i + 1] -= s11;
+        if(ti > tc) S.D[(c + 1) * DSB + i] -= s01;
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// Off-diagonal 16 x 16 blocks of the 128 x 128 inverse from the factor (lower slots of S.D) and the 16 x 16 diagonal inverses:
+// block row a: Inv_ab = -Inv_aa * sum_{q=b}^{a-1} L_aq Inv_qb.
+__device__ void invert_block128(DiagSmem& S)
+{
+  const int tid = threadIdx.x;
+  for(int a = 1; a < BB / 16; a++) {
+    const int ncol = 16 * a;
+    for(int e = tid; e < 16 * ncol; e += blockDim.x) {
+      const int r = e & 15, c = e >> 4;
+      const int ra = ncol + r;
+      double acc = S.D[c * DSB + ra] * S.idg[c];
+      for(int q = c + 1; q < ncol; q++) acc += S.D[q * DSB + ra] * S.D[q * DSB + c];
+      S.Tt[c * 17 + r] = acc;
+    }
+    __syncthreads();
+    const double* inv = S.Inv16 + a * 16 * 17;
+    for(int e = tid; e < 16 * ncol; e += blockDim.x) {
+      const int r = e & 15, c = e >> 4;
+      double acc = 0.0;
+#pragma unroll
+      for(int q = 0; q < 16; q++)
+        if(q <= r) acc += inv[r * 17 + q] * S.Tt[c * 17 + q];
+      S.D[(ncol + r) * DSB + c] = -acc;
+    }
+    __syncthreads();
+  }
+}
+
+__device__ void store_inverse128(const DiagSmem& S, double* __restrict__ InvG)
+{
+  for(int e = threadIdx.x; e < BB * BB; e += blockDim.x) {
+    const int r = e % BB, c = e / BB;
+    InvG[e] = r > c ? S.D[r * DSB + c] : (r == c ? S.idg[r] : 0.0);
+  }
+}
+
+template <bool LDL>
+__global__ void __launch_bounds__(DTHREADS, 1)
+k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restrict__ InvG, double* __restrict__ dinvG, int* __restrict__ info)
+{
+  extern __shared__ __align__(16) unsigned char dsm_raw[];
+  DiagSmem& S = *reinterpret_cast<DiagSmem*>(dsm_raw);
+  const int tid = threadIdx.x;
+  const int nb = min(BB, N - k0);
+  for(int e = tid; e < BB * BB; e += DTHREADS) {
+    const int j = e / BB, i = e % BB;
+    double v = (i == j) ? 1.0 : 0.0;
+    if(i < nb && j < nb && i >= j) v = LC(A, lda, k0 + i, k0 + j);
+    S.D[j * DSB + i] = v;
+  }
+  __syncthreads();
+  factor_block128<LDL>(S, k0, info);
+  for(int e = tid; e < nb * nb; e += DTHREADS) {
+    const int j = e / nb, i = e % nb;
+    if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DSB + i];
+  }
+  if(LDL && tid < BB) dinvG[tid] = S.rdv[tid];
+  invert_block128(S);
+  store_inverse128(S, InvG);
+}
+
+// Inverses of the 128 x 128 diagonal triangles of an EXISTING factor (paths that do not run k_diag128: cooperative Cholesky,
+// Bunch-Kaufman). unit: the factor has an implicit unit diagonal (the stored diagonal holds D and is ignored).
+__global__ void __launch_bounds__(DTHREADS, 1)
+k_block_inverses(const double* __restrict__ F, long long ldf, int N, int unit, double* __restrict__ InvAll)
+{
+  extern __shared__ __align__(16) unsigned char dsm_raw[];
+  DiagSmem& S = *reinterpret_cast<DiagSmem*>(dsm_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = blockIdx.x * BB;
+  const int nb = min(BB, N - k0);
+  for(int e = tid; e < BB * BB; e += DTHREADS) {
+    const int j = e / BB, i = e % BB;
+    double v = 0.0;
+    if(i < nb && j < nb && i > j) v = LC(F, ldf, k0 + i, k0 + j);
+    if(i == j) v = (i < nb && !unit) ? LC(F, ldf, k0 + i, k0 + i) : 1.0;
+    if(i < j) v = 0.0;
+    S.D[j * DSB + i] = v;
+  }
+  __syncthreads();
+  if(tid < BB) S.idg[tid] = 1.0 / S.D[tid * DSB + tid];
+  __syncthreads();
+  // 16 x 16 diagonal inverses: warp w < 8 handles triangle w, lane = column of the inverse
+  if(warp < 8) {
+    const int c0 = warp * 16;
+    double x[16], sacc[16];
+#pragma unroll
+    for(int r = 0; r < 16; r++) { x[r] = 0.0; sacc[r] = 0.0; }
+#pragma unroll
+    for(int q = 0; q < 16; q++) {
+      const double rq = S.idg[c0 + q];
+      if(q == lane) x[q] = rq;
+      else if(q > lane) x[q] = -sacc[q] * rq;
+#pragma unroll
+      for(int r = q + 1; r < 16; r++) sacc[r] += S.D[(c0 + q) * DSB + c0 + r] * x[q];
+    }
+    __syncwarp();
+    if(lane < 16) {
+      double* inv = S.Inv16 + warp * 16 * 17;
+#pragma unroll
+      for(int r = 0; r < 16; r++) {
+        inv[r * 17 + lane] = x[r];
+        if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r];
+      }
+    }
+  }
+  __syncthreads();
+  invert_block128(S);
+  store_inverse128(S, InvAll + (size_t)blockIdx.x * BB * BB);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Blocked solves. SB rows per launch; the stored inverses make the in-block solves matrix-vector products.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SB = 256;
+constexpr int ST = 1024;
+
+struct StepSmem
+{
+  double xs[64];
+  double red[ST];
+  double y[SB];
+  double xo[SB];
+  int last;
+};
+
+// sub-block products of the last CTA. y (S.y) holds b - (outside contributions); on exit S.xo holds the solution of the step.
+__device__ void fwd_tail(StepSmem& S, const double* __restrict__ F, long long ldf, int k0, int nrows, const double* __restrict__ InvAll)
+{
+  const int tid = threadIdx.x;
+  const int nsub = (nrows + BB - 1) / BB;
+  const int r = tid & 127, gsel = tid >> 7; // 8 groups
+  for(int s = 0; s < nsub; s++) {
+    const int rows = min(BB, nrows - s * BB);
+    if(s > 0) { // y_s -= L(s, 0:s) x_(0:s)
+      const int ncols = s * BB;
+      double acc = 0.0;
+      if(r < rows)
+        for(int j = gsel; j < ncols; j += 8) acc += LC(F, ldf, k0 + s * BB + r, k0 + j) * S.xo[j];
+      S.red[tid] = acc;
+      __syncthreads();
+      if(tid < rows) {
+        double t = 0.0;
+#pragma unroll
+        for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
+        S.y[s * BB + tid] -= t;
+      }
+      __syncthreads();
+    }
+    // x_s = Inv_s y_s  (Inv(r,c) at c*128 + r, lower triangular)
+    const double* Inv = InvAll + (size_t)(k0 / BB + s) * BB * BB;
+    double acc = 0.0;
+    for(int cc = gsel; cc <= r; cc += 8) acc += Inv[cc * BB + r] * S.y[s * BB + cc];
+    S.red[tid] = acc;
+    __syncthreads();
+    if(tid < BB) {
+      double t = 0.0;
+#pragma unroll
+      for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
+      S.xo[s * BB + tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(ST, 1)
+k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, const double* __restrict__ InvAll, double* __restrict__ x,
+                 double* __restrict__ partial, int* __restrict__ counter)
+{
+  __shared__ StepSmem S;
+  const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+  const int nrows = min(SB, N - k0);
+  const int r = tid & 255, gsel = tid >> 8; // 4 column groups of 16
+  if(k0 > 0) {
+    const int jb = b * 64;
+    if(tid < 64) S.xs[tid] = (jb + tid < k0) ? x[jb + tid] : 0.0;
+    __syncthreads();
+    double acc = 0.0;
+    if(r < nrows) {
+      double v[16];
+#pragma unroll
+      for(int q = 0; q < 16; q++) {
+        const int j = jb + gsel * 16 + q;
+        v[q] = j < k0 ? LC(F, ldf, k0 + r, j) : 0.0;
+      }
+#pragma unroll
+      for(int q = 0; q < 16; q++) acc += v[q] * S.xs[gsel * 16 + q];
+    }
+    S.red[tid] = acc;
+    __syncthreads();
+    if(tid < SB) partial[(size_t)b * SB + tid] = (S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid]);
+  }
+  __threadfence();
+  __syncthreads();
+  if(tid == 0) S.last = (atomicAdd(counter, 1) == G - 1);
+  __syncthreads();
+  if(!S.last) return;
+  __threadfence();
+  {
+    double acc = 0.0;
+    if(k0 > 0 && r < nrows)
+      for(int c = gsel; c < G; c += 4) acc += __ldcg(&partial[(size_t)c * SB + r]);
+    S.red[tid] = acc;
+    __syncthreads();
+    if(tid < SB) S.y[tid] = tid < nrows ? x[k0 + tid] - ((S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid])) : 0.0;
+    __syncthreads();
+  }
+  fwd_tail(S, F, ldf, k0, nrows, InvAll);
+  if(tid < nrows) x[k0 + tid] = S.xo[tid];
+  if(tid == 0) *counter = 0;
+}
+
+// backward: rows [k0, k0+nrows) of L^T x = z; rows >= k1 = k0 + nrows are solved already
+__global__ void __launch_bounds__(ST, 1)
+k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, const double* __restrict__ InvAll, double* __restrict__ x,
+                 double* __restrict__ partial, int* __restrict__ counter)
+{
+  __shared__ StepSmem S;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
+  const int nrows = min(SB, N - k0);
+  const int k1 = k0 + nrows;
+  if(k1 < N) {
+    const int il = tid & 63, cg = tid >> 6; // 64 rows x 16 column groups of 16
+    const int i = k1 + b * 64 + il;
+    const double xi = i < N ? x[i] : 0.0;
+    double v[16];
+#pragma unroll
+    for(int q = 0; q < 16; q++) {
+      const int jl = cg * 16 + q;
+      v[q] = (i < N && jl < nrows) ? LC(F, ldf, i, k0 + jl) * xi : 0.0;
+    }
+#pragma unroll
+    for(int q = 0; q < 16; q++) v[q] = hb_warp_sum(v[q]);
+    if(lane == 0) {
+#pragma unroll
+      for(int q = 0; q < 16; q++) S.red[warp * 16 + q] = v[q];
+    }
+    __syncthreads();
+    if(tid < SB) { // column tid: group tid/16 -> warps 2*(tid/16), 2*(tid/16)+1
+      const int cgi = tid >> 4, q = tid & 15;
+      partial[(size_t)b * SB + tid] = S.red[(2 * cgi) * 16 + q] + S.red[(2 * cgi + 1) * 16 + q];
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if(tid == 0) S.last = (atomicAdd(counter, 1) == G - 1);
+  __syncthreads();
+  if(!S.last) return;
+  __threadfence();
+  {
+    const int r = tid & 255, gsel = tid >> 8;
+    double acc = 0.0;
+    if(k1 < N && r < nrows)
+      for(int c = gsel; c < G; c += 4) acc += __ldcg(&partial[(size_t)c * SB + r]);
+    S.red[tid] = acc;
+    __syncthreads();
+    if(tid < SB) S.y[tid] = tid < nrows ? x[k0 + tid] - ((S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid])) : 0.0;
+    __syncthreads();
+  }
+  const int nsub = (nrows + BB - 1) / BB;
+  for(int s = nsub - 1; s >= 0; s--) {
+    const int cols = min(BB, nrows - s * BB);
+    // y_s -= L(t, s)^T x_t for the sub-blocks t > s of this step; then x_s = Inv_s^T y_s. One warp per column (4 columns per warp).
+    for(int cc = warp; cc < cols; cc += ST / 32) {
+      const int jl = s * BB + cc;
+      double acc = 0.0;
+      for(int il2 = (s + 1) * BB + lane; il2 < nrows; il2 += 32) acc += LC(F, ldf, k0 + il2, k0 + jl) * S.xo[il2];
+      acc = hb_warp_sum(acc);
+      if(lane == 0) S.y[jl] -= acc;
+    }
+    __syncthreads();
+    const double* Inv = InvAll + (size_t)(k0 / BB + s) * BB * BB;
+    for(int cc = warp; cc < BB; cc += ST / 32) {
+      double acc = 0.0;
+      for(int rr = cc + lane; rr < BB; rr += 32) acc += Inv[cc * BB + rr] * S.y[s * BB + rr];
+      acc = hb_warp_sum(acc);
+      if(lane == 0) S.xo[s * BB + cc] = acc;
+    }
+    __syncthreads();
+  }
+  if(tid < nrows) x[k0 + tid] = S.xo[tid];
+  if(tid == 0) *counter = 0;
+}
+
+// block-diagonal solve between the sweeps: LDL^T without pivoting (ipiv == NULL: 1x1 blocks) or Bunch-Kaufman (2x2 blocks flagged
+// by ipiv[k] < 0 on both rows, LAPACK convention; the sub-diagonal entry of the block is F(k+1,k))
+__global__ void k_dsolve(const double* __restrict__ F, long long ldf, int N, const int* __restrict__ ipiv, double* __restrict__ x)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= N) return;
+  if(!ipiv || ipiv[k] > 0) {
+    x[k] = x[k] / LC(F, ldf, k, k);
+    return;
+  }
+  // 2x2 block: handled by its first row
+  if(k > 0 && ipiv[k - 1] < 0) {
+    // is k the second row of a block? count the run of negatives ending at k-1
+    int run = 0;
+    for(int q = k - 1; q >= 0 && ipiv[q] < 0; q--) run++;
+    if(run & 1) return;
+  }
+  const double akm1k = LC(F, ldf, k + 1, k);
+  const double akm1 = LC(F, ldf, k, k) / akm1k;
+  const double ak = LC(F, ldf, k + 1, k + 1) / akm1k;
+  const double denom = akm1 * ak - 1.0;
+  const double bkm1 = x[k] / akm1k, bk = x[k + 1] / akm1k;
+  x[k] = (ak * bkm1 - bk) / denom;
+  x[k + 1] = (akm1 * bk - bkm1) / denom;
+}
+
+__global__ void k_gather(int N, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < N) out[i] = in[perm[i]];
+}
+__global__ void k_scatter(int N, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if(i < N) out[perm[i]] = in[i];
+}
+
+bool g_big_attr[16] = {false};
+
+int ensure_attrs(hb_ctx* c)
+{
+  if(c->device < 16 && g_big_attr[c->device]) return HB_OK;
+  HB_CUDA(cudaFuncSetAttribute(k_gemm_pq<64, EPI_SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<64>::SMEM));
+  HB_CUDA(cudaFuncSetAttribute(k_gemm_pq<128, EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<128>::SMEM));
+  HB_CUDA(cudaFuncSetAttribute(k_gemm_pq<128, EPI_STORE_LDL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GemmCfg<128>::SMEM));
+  HB_CUDA(cudaFuncSetAttribute(k_diag128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+  HB_CUDA(cudaFuncSetAttribute(k_diag128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+  HB_CUDA(cudaFuncSetAttribute(k_block_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+  if(c->device < 16) g_big_attr[c->device] = true;
+  return HB_OK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// internal API (hb_dense.cuh)
+// ---------------------------------------------------------------------------------------------------------------------
+int hb_big_init(hb_ctx* c, hb_big* b)
+{
+  HB_CHECK(ensure_attrs(c));
+  if(!b->panel_stream) {
+    int lo = 0, hi = 0;
+    HB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    HB_CUDA(cudaStreamCreateWithPriority(&b->panel_stream, cudaStreamNonBlocking, hi));
+    HB_CUDA(cudaEventCreateWithFlags(&b->ev_panel, cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&b->ev_upd, cudaEventDisableTiming));
+  }
+  return HB_OK;
+}
+
+void hb_big_release(hb_big* b)
+{
+  if(b->panel_stream) {
+    cudaStreamSynchronize(b->panel_stream);
+    cudaStreamDestroy(b->panel_stream);
+    cudaEventDestroy(b->ev_panel);
+    cudaEventDestroy(b->ev_upd);
+    b->panel_stream = nullptr;
+  }
+  cudaFree(b->InvAll); cudaFree(b->W[0]); cudaFree(b->W[1]); cudaFree(b->dinv); cudaFree(b->partial); cudaFree(b->counter); cudaFree(b->xtmp);
+  b->InvAll = b->W[0] = b->W[1] = b->dinv = b->partial = b->xtmp = nullptr;
+  b->counter = nullptr;
+  b->capN = 0;
+}
+
+int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w)
+{
+  HB_CHECK(hb_big_init(c, b));
+  const int nblk = (N + BB - 1) / BB;
+  if(b->capN < N) {
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(b->InvAll); cudaFree(b->partial); cudaFree(b->xtmp); cudaFree(b->W[0]); cudaFree(b->W[1]);
+    b->W[0] = b->W[1] = nullptr;
+    if(cudaMalloc(&b->InvAll, sizeof(double) * (size_t)nblk * BB * BB) != cudaSuccess || cudaMalloc(&b->partial, sizeof(double) * (size_t)(N / 64 + 2) * SB) != cudaSuccess ||
+       cudaMalloc(&b->xtmp, sizeof(double) * (size_t)(N + 2)) != cudaSuccess) {
+      cudaGetLastError();
+      return hb_fail(HB_ERR_ALLOC, "hb_big_reserve: scratch allocation failed%s", "");
+    }
+    if(!b->dinv) HB_CUDA(cudaMalloc(&b->dinv, sizeof(double) * BB));
+    if(!b->counter) {
+      HB_CUDA(cudaMalloc(&b->counter, sizeof(int) * 4));
+      HB_CUDA(cudaMemsetAsync(b->counter, 0, sizeof(int) * 4, c->stream));
+    }
+    b->capN = N;
+  }
+  if(need_w && !b->W[0]) {
+    const size_t ldw = (size_t)((N + 7) & ~7);
+    if(cudaMalloc(&b->W[0], sizeof(double) * ldw * BB) != cudaSuccess || cudaMalloc(&b->W[1], sizeof(double) * ldw * BB) != cudaSuccess) {
+      cudaGetLastError();
+      return hb_fail(HB_ERR_ALLOC, "hb_big_reserve: panel scratch allocation failed%s", "");
+    }
+  }
+  return HB_OK;
+}
+
+// Cholesky (ldl = false) or no-pivot LDL^T (ldl = true) of the column-major-lower triangle; lda must be even and A 16-byte aligned.
+// info_dev: 0 ok, k > 0 = breakdown at column k (1-based). The diagonal-block inverses land in b->InvAll.
+int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ldl, int* info_dev)
+{
+  HB_REQUIRE((lda & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0, "hb_big_factor: needs an even leading dimension and a 16-byte aligned matrix");
+  HB_CHECK(hb_big_reserve(c, b, N, ldl));
+  const long long ldw = (N + 7) & ~7;
+  cudaStream_t su = c->stream, sp = b->panel_stream;
+  HB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), su));
+  HB_CUDA(cudaEventRecord(b->ev_upd, su));
+  const int nblk = (N + BB - 1) / BB;
+  for(int blk = 0; blk < nblk; blk++) {
+    const int k0 = blk * BB, nb = N - k0 < BB ? N - k0 : BB, r0 = k0 + nb;
+    double* InvG = b->InvAll + (size_t)blk * BB * BB;
+    double* Wb = ldl ? b->W[blk & 1] : nullptr;
+    // ---- panel stream: diagonal block, then L21 ----
+    HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd, 0));
+    if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev);
+    else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev);
+    HB_LAUNCHED();
+    if(r0 < N) {
+      GemmArgs g{};
+      g.P = A + (size_t)k0 * lda; g.ldp = lda;
+      g.Q = InvG; g.ldq = BB; g.qsub = k0;
+      g.kb = nb;
+      g.C = A; g.ldc = lda;
+      g.i_base = r0; g.j_base = k0; g.i_end = N; g.j_end = r0; g.tj0 = 0;
+      g.W2 = Wb; g.ldw2 = ldw; g.dinv = b->dinv; g.state = nullptr;
+      const dim3 grid((N - r0 + TM - 1) / TM, 1);
+      if(ldl) k_gemm_pq<128, EPI_STORE_LDL><<<grid, 256, GemmCfg<128>::SMEM, sp>>>(g);
+      else k_gemm_pq<128, EPI_STORE><<<grid, 256, GemmCfg<128>::SMEM, sp>>>(g);
+      HB_LAUNCHED();
+    }
+    HB_CUDA(cudaEventRecord(b->ev_panel, sp));
+    HB_CUDA(cudaStreamWaitEvent(su, b->ev_panel, 0));
+    if(r0 < N) {
+      // ---- update stream: next panel's columns first, then the rest ----
+      GemmArgs g{};
+      g.P = ldl ? Wb : A + (size_t)k0 * lda; g.ldp = ldl ? ldw : lda;
+      g.Q = A + (size_t)k0 * lda; g.ldq = lda; g.qsub = 0;
+      g.kb = nb;
+      g.C = A; g.ldc = lda;
+      g.i_base = r0; g.j_base = r0; g.i_end = N; g.j_end = N; g.tj0 = 0;
+      g.W2 = nullptr; g.ldw2 = 0; g.dinv = nullptr; g.state = nullptr;
+      const int nti = (N - r0 + TM - 1) / TM;
+      const int ntj = (N - r0 + 63) / 64;
+      k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj < 2 ? ntj : 2), 256, GemmCfg<64>::SMEM, su>>>(g);
+      HB_LAUNCHED();
+      HB_CUDA(cudaEventRecord(b->ev_upd, su));
+      if(ntj > 2) {
+        g.tj0 = 2;
+        k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj - 2), 256, GemmCfg<64>::SMEM, su>>>(g);
+        HB_LAUNCHED();
+      }
+    }
+  }
+  b->inv_valid = true;
+  return HB_OK;
+}
+
+// trailing update of a pivoted panel whose origin / width live in device memory (state[0] = k0, state[1] = kb): A22 -= W21 L21^T
+int hb_big_trailing_from_state(hb_ctx* c, int N, double* A, long long lda, const double* W, long long ldw, const int* state_dev, int r0_min, cudaStream_t st)
+{
+  HB_CHECK(ensure_attrs(c));
+  if(r0_min >= N) return HB_OK;
+  GemmArgs g{};
+  g.P = W; g.ldp = ldw; g.Q = nullptr; g.ldq = lda; g.qsub = 0; g.kb = 0;
+  g.C = A; g.ldc = lda;
+  g.i_base = g.j_base = r0_min; g.i_end = N; g.j_end = N; g.tj0 = 0;
+  g.state = state_dev;
+  const int nti = (N - r0_min + TM - 1) / TM, ntj = (N - r0_min + 63) / 64;
+  k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj), 256, GemmCfg<64>::SMEM, st>>>(g);
+  HB_LAUNCHED();
+  return HB_OK;
+}
+
+// 128 x 128 diagonal-block inverses of a factor produced by another path
+int hb_big_block_inverses(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, bool unit)
+{
+  HB_CHECK(hb_big_reserve(c, b, N, false));
+  const int nblk = (N + BB - 1) / BB;
+  const int u = unit ? 1 : 0;
+  k_block_inverses<<<nblk, DTHREADS, sizeof(DiagSmem), c->stream>>>(F, ldf, N, u, b->InvAll);
+  HB_LAUNCHED();
+  b->inv_valid = true;
+  return HB_OK;
+}
+
+// x <- solution of (L [D] L^T) x = x with the factor F (+ b->InvAll). dmode: 0 = Cholesky (no D), 1 = D from the diagonal (LDL^T),
+// 2 = Bunch-Kaufman block diagonal (ipiv_dev), perm_dev (may be NULL): x is gathered through it first and scattered back at the end.
+int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const int* perm_dev, double* x)
+{
+  HB_REQUIRE(b->inv_valid && b->capN >= N, "hb_big_solve: no block inverses for this factor");
+  if(N == 0) return HB_OK;
+  cudaStream_t st = c->stream;
+  double* v = x;
+  if(perm_dev) {
+    k_gather<<<(N + 255) / 256, 256, 0, st>>>(N, perm_dev, x, b->xtmp);
+    HB_LAUNCHED();
+    v = b->xtmp;
+  }
+  for(int k0 = 0; k0 < N; k0 += SB) {
+    const int G = k0 > 0 ? (k0 + 63) / 64 : 1;
+    k_solve_fwd_step<<<G, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    HB_LAUNCHED();
+  }
+  if(dmode != 0) {
+    k_dsolve<<<(N + 127) / 128, 128, 0, st>>>(F, ldf, N, dmode == 2 ? ipiv_dev : nullptr, v);
+    HB_LAUNCHED();
+  }
+  const int last = ((N - 1) / SB) * SB;
+  for(int k0 = last; k0 >= 0; k0 -= SB) {
+    const int nrows = N - k0 < SB ? N - k0 : SB;
+    const int below = N - (k0 + nrows);
+    const int G = below > 0 ? (below + 63) / 64 : 1;
+    k_solve_bwd_step<<<G, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    HB_LAUNCHED();
+  }
+  if(perm_dev) {
+    k_scatter<<<(N + 255) / 256, 256, 0, st>>>(N, perm_dev, b->xtmp, x);
+    HB_LAUNCHED();
+  }
+  return HB_OK;
+}

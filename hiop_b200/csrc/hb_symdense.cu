@@ -2,6 +2,7 @@
 // src/LinAlg/hiopLinSolverSymDenseLapack.hpp:75-192 and the MAGMA twins hiopLinSolverSymDenseMagma.cpp:120-270, 324-476.
 #include "hb_common.cuh"
 #include "hb_dense.cuh"
+#include <cstdlib>
 
 struct hb_symdense
 {
@@ -10,6 +11,12 @@ struct hb_symdense
   double* M = nullptr;      // N x N row-major, upper triangle valid on entry, factor in place
   double* W = nullptr;      // panel scratch (lazy)
   double* xbuf = nullptr;   // staging for the *_host variants (lazy)
+  size_t xbuf_cap = 0;      // doubles allocated in xbuf (per handle)
+  double* Fpad = nullptr;   // odd N: copy of M with an even leading dimension (the large-N kernels use 16-byte accesses)
+  double* F = nullptr;      // where the current factor lives (M or Fpad)
+  long long ldf = 0;
+  hb_big big;               // large-N path: streams, diagonal-block inverses, solve scratch
+  bool big_solve = false;   // the current factor is solved with hb_big_solve
   int* ipiv = nullptr;
   int* info = nullptr;      // device: [0] info, [1..3] inertia
   int* info_host = nullptr; // pinned
@@ -20,6 +27,15 @@ struct hb_symdense
 
 namespace {
 constexpr int BLOCKED_BK_MIN_N = 96; // below this the one-CTA unblocked DSYTF2 kernel is faster than panel + trailing launches
+// Cholesky / no-pivot LDL^T: from this N on the look-ahead path of hb_dense_big.cu factors (below: cooperative / per-panel kernels);
+// from BIG_SOLVE_MIN_N on the blocked multi-CTA solve replaces the one-CTA sweeps. HB_DENSE_BIG_MIN overrides the first (benchmarks).
+int big_factor_min(int mode)
+{
+  static const int env = getenv("HB_DENSE_BIG_MIN") ? atoi(getenv("HB_DENSE_BIG_MIN")) : -1;
+  if(env >= 0) return env;
+  return mode == HB_FACT_CHOLESKY ? 1025 : 257;
+}
+constexpr int BIG_SOLVE_MIN_N = 257;
 }
 
 extern "C" int hb_symdense_create(hb_ctx* c, int N, hb_symdense** out)
@@ -47,7 +63,8 @@ extern "C" int hb_symdense_destroy(hb_symdense* s)
   if(!s) return HB_OK;
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
-  cudaFree(s->M); cudaFree(s->W); cudaFree(s->xbuf); cudaFree(s->ipiv); cudaFree(s->info);
+  hb_big_release(&s->big);
+  cudaFree(s->M); cudaFree(s->W); cudaFree(s->xbuf); cudaFree(s->ipiv); cudaFree(s->info); cudaFree(s->Fpad);
   cudaFreeHost(s->info_host);
   delete s;
   return HB_OK;
@@ -65,20 +82,40 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
   s->factored = false;
   if(N == 0) { s->factored = true; s->n_neg = s->n_null = s->n_pos = 0; return 0; }
   HB_CUDA(cudaMemsetAsync(s->info, 0, sizeof(int) * 4, c->stream));
+  s->F = s->M; s->ldf = N; s->big_solve = false; s->big.inv_valid = false;
   const bool blocked_bk = (mode == HB_FACT_BUNCH_KAUFMAN && N >= BLOCKED_BK_MIN_N);
+  const bool big = (mode != HB_FACT_BUNCH_KAUFMAN && N >= big_factor_min(mode));
+  if(big) {
+    if(N & 1) { // even leading dimension for the 16-byte operand copies
+      const long long ld = (N + 7) & ~7LL;
+      if(!s->Fpad) {
+        if(cudaMalloc(&s->Fpad, sizeof(double) * (size_t)ld * N) != cudaSuccess) { cudaGetLastError(); return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate the padded factor%s", ""); }
+        HB_CUDA(cudaMemsetAsync(s->Fpad, 0, sizeof(double) * (size_t)ld * N, c->stream));
+      }
+      HB_CUDA(cudaMemcpy2DAsync(s->Fpad, sizeof(double) * ld, s->M, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyDeviceToDevice, c->stream));
+      s->F = s->Fpad; s->ldf = ld;
+    }
+    HB_CHECK(hb_big_factor(c, &s->big, N, s->F, s->ldf, mode == HB_FACT_NOPIV, s->info));
+    s->big_solve = true;
+  } else
   if((mode == HB_FACT_NOPIV || blocked_bk) && !s->W) {
     if(cudaMalloc(&s->W, sizeof(double) * (size_t)2 * 64 * N) != cudaSuccess) {
       cudaGetLastError();
       return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate panel scratch%s", "");
     }
   }
-  if(mode == HB_FACT_BUNCH_KAUFMAN) {
+  if(big) {
+  } else if(mode == HB_FACT_BUNCH_KAUFMAN) {
     if(blocked_bk) HB_CHECK(hb_dense_sytrf_blocked(c, N, s->M, N, s->ipiv, s->W, s->info));
     else HB_CHECK(hb_dense_sytf2(c, N, s->M, N, s->ipiv, s->info));
   } else {
     HB_CHECK(hb_dense_factor_blocked(c, N, s->M, N, mode == HB_FACT_NOPIV, s->W, s->info));
+    if(N >= BIG_SOLVE_MIN_N) { // factor from the cooperative / per-panel kernels, solves through the blocked multi-CTA path
+      HB_CHECK(hb_big_block_inverses(c, &s->big, N, s->M, N, mode == HB_FACT_NOPIV));
+      s->big_solve = true;
+    }
   }
-  HB_CHECK(hb_dense_inertia(c, N, s->M, N, s->ipiv, mode, s->info + 1));
+  HB_CHECK(hb_dense_inertia(c, N, s->F, (int)s->ldf, s->ipiv, mode, s->info + 1));
   HB_CUDA(cudaMemcpyAsync(s->info_host, s->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   s->n_neg = s->info_host[1]; s->n_null = s->info_host[2]; s->n_pos = s->info_host[3];
@@ -104,7 +141,10 @@ extern "C" int hb_symdense_solve(hb_symdense* s, double* x, int nrhs)
   HB_REQUIRE(x, "hb_symdense_solve: null rhs");
   if(!s->factored) return hb_fail(HB_ERR_STATE, "hb_symdense_solve: no valid factorization (call hb_symdense_matrix_changed)%s", "");
   hb_ctx* c = s->ctx;
-  if(s->mode == HB_FACT_BUNCH_KAUFMAN) {
+  if(s->big_solve) {
+    for(int r = 0; r < nrhs; r++)
+      HB_CHECK(hb_big_solve(c, &s->big, s->N, s->F, s->ldf, s->mode == HB_FACT_CHOLESKY ? 0 : 1, nullptr, nullptr, x + (size_t)r * s->N));
+  } else if(s->mode == HB_FACT_BUNCH_KAUFMAN) {
     HB_CHECK(hb_dense_sytrs(c, s->N, s->M, s->N, s->ipiv, x, s->N, nrhs));
   } else {
     for(int r = 0; r < nrhs; r++) HB_CHECK(hb_dense_tri_solve(c, s->N, s->M, s->N, s->mode == HB_FACT_NOPIV, x + (size_t)r * s->N));
@@ -123,13 +163,13 @@ extern "C" int hb_symdense_solve_host(hb_symdense* s, double* x_host, int nrhs)
 {
   HB_REQUIRE(s && nrhs >= 0, "hb_symdense_solve_host: bad arguments");
   if(s->N == 0 || nrhs == 0) return 1;
+  HB_REQUIRE(x_host, "hb_symdense_solve_host: null rhs");
   hb_ctx* c = s->ctx;
-  static thread_local size_t cap = 0;
   const size_t need = (size_t)s->N * nrhs;
-  if(!s->xbuf || cap < need) {
+  if(!s->xbuf || s->xbuf_cap < need) {
     if(s->xbuf) { HB_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(s->xbuf); s->xbuf = nullptr; }
     if(cudaMalloc(&s->xbuf, sizeof(double) * need) != cudaSuccess) { cudaGetLastError(); return hb_fail(HB_ERR_ALLOC, "rhs staging allocation failed%s", ""); }
-    cap = need;
+    s->xbuf_cap = need;
   }
   HB_CUDA(cudaMemcpyAsync(s->xbuf, x_host, sizeof(double) * need, cudaMemcpyHostToDevice, c->stream));
   int rc = hb_symdense_solve(s, s->xbuf, nrhs);
