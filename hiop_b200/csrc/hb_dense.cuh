@@ -41,6 +41,16 @@ int hb_big_init(hb_ctx* c, hb_big* b);
 void hb_big_release(hb_big* b);
 int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w);
 int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ldl, int* info_dev);
+int hb_big_diag_profile(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int k0, bool ldl, long long* prof_host8);
 int hb_big_trailing_from_state(hb_ctx* c, int N, double* A, long long lda, const double* W, long long ldw, const int* state_dev, int r0_min, cudaStream_t st);
 int hb_big_block_inverses(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, bool unit);
-int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const int* perm_dev, double* x);
+int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const double* dsub_dev, const int* perm_dev,
+                 double* x);
+// cluster Bunch-Kaufman (hb_bk_cluster.cu)
+bool hb_bkc_supported(hb_ctx* c, int N);
+int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ipiv_dev, double* dsub_dev, int* perm_dev, double* Wp, long long ldw,
+                  int* state_dev, int* swaplog_dev, int* info_dev);
+int hb_bkc_inertia(hb_ctx* c, int N, const double* F, long long ldf, const int* ipiv_dev, const double* dsub_dev, int* out3_dev);
+int hb_bkc_dsolve(hb_ctx* c, int N, const double* F, long long ldf, const int* ipiv_dev, const double* dsub_dev, double* x);
+int hb_bkc_profile(hb_ctx* c, int on, long long* prof_host8);
+#define HB_BKC_SWAPLOG_INTS(N) ((size_t)((N) / 7 + 4) * 68)

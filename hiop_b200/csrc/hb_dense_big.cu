@@ -230,23 +230,32 @@ __global__ void __launch_bounds__(256, (TN == 64 ? 2 : 1)) k_gemm_pq(const GemmA
 // ---------------------------------------------------------------------------------------------------------------------
 // 128 x 128 diagonal block: factor (LL^T or LDL^T without pivoting) + inverse of the triangular factor, one CTA.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int DSB = BB + 1;
+constexpr int DSB = BB + 4; // 132: the m8n8k4 fragment reads (4 k-rows x 8 consecutive entries) are bank-conflict free
+constexpr int TLD = 116;
 constexpr int DTHREADS = 512;
 struct DiagSmem
 {
   double D[BB * DSB];        // D[j*DSB + i] = element (i,j), i >= j; the slots i < j receive the strictly lower part of the inverse:
                              // Inv(r,c), r > c, lives at D[r*DSB + c]
   double Inv16[8 * 16 * 17]; // inverses of the eight 16 x 16 diagonal triangles
-  double Tt[112 * 17];
+  double Tt[16 * TLD];
   double idg[BB];            // diagonal of the inverse (1/L_rr; 1 for the unit factor of LDL^T)
   double dv[BB];             // LDL^T: d_j
   double rdv[BB];            // LDL^T: 1/d_j
 };
 
+// Factors the 128 x 128 block in S.D (16-wide sub-panels). Per sub-panel: warp 0 factors the 16 x 16 diagonal triangle in registers
+// and inverts it; the rows below and the rank-16 update of the rest run on the DMMA pipe straight out of shared memory (the first
+// version did them with scalar FMAs on 2 x 2 register tiles and was bound by shared-memory wavefronts: 86 us per block).
+// InvG (global, column-major 128 x 128, zero above the diagonal from allocation): receives the 16 x 16 diagonal inverses here and the
+// off-diagonal blocks in invert_block128.
 template <bool LDL>
-__device__ void factor_block128(DiagSmem& S, int k0, int* info)
+__device__ void factor_block128(DiagSmem& S, int k0, int* info, double* __restrict__ InvG, long long* prof)
 {
+  long long q0 = prof ? clock64() : 0;
+#define QP(slot) if(prof && threadIdx.x == 0) { const long long q1 = clock64(); prof[slot] += q1 - q0; q0 = q1; }
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t4 = lane & 3;
   for(int kb = 0; kb < BB / 16; kb++) {
     const int c0 = kb * 16;
     if(warp == 0) {
@@ -258,7 +267,7 @@ __device__ void factor_block128(DiagSmem& S, int k0, int* info)
 #define BIG_CHOL_COL(j)                                                                          \
   {                                                                                              \
     const double d = __shfl_sync(0xffffffffu, a[j], j);                                          \
-    if(!(d > 0.0) && lane == 0) atomicCAS(info, 0, k0 + c0 + j + 1);                             \
+    if(!(d > 0.0) && lane == 0 && info) atomicCAS(info, 0, k0 + c0 + j + 1);                     \
     const double r = rsqrt(d);                                                                   \
     if(lane == j) { a[j] = d * r; myr = r; }                                                     \
     else if(lane > j) a[j] *= r;                                                                 \
@@ -270,7 +279,7 @@ __device__ void factor_block128(DiagSmem& S, int k0, int* info)
 #define BIG_LDL_COL(j)                                                                           \
   {                                                                                              \
     const double d = __shfl_sync(0xffffffffu, a[j], j);                                          \
-    if((d == 0.0 || d != d) && lane == 0) atomicCAS(info, 0, k0 + c0 + j + 1);                   \
+    if((d == 0.0 || d != d) && lane == 0 && info) atomicCAS(info, 0, k0 + c0 + j + 1);           \
     const double r = 1.0 / d;                                                                    \
     const double wj = a[j];                                                                      \
     if(lane > j) a[j] = wj * r;                                                                  \
@@ -322,101 +331,111 @@ __device__ void factor_block128(DiagSmem& S, int k0, int* info)
           for(int r = 0; r < 16; r++) {
             inv[r * 17 + lane] = x[r];
             if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r]; // strictly lower part of the inverse -> the unused upper slots
+            if(r >= lane) InvG[(size_t)(c0 + lane) * BB + c0 + r] = x[r];
           }
         }
       }
     }
     __syncthreads();
+    QP(1);
     const int below = BB - c0 - 16;
     {
+      // rows below: X = A(:, c0:c0+16) T^-T [ D^-1 ], 8 rows x 16 columns per warp (both column tiles, so the in-place write is safe)
       const double* inv = S.Inv16 + kb * 16 * 17;
-      double y[4];
+      for(int rg = warp; rg < below / 8; rg += DTHREADS / 32) {
+        const int r0 = c0 + 16 + rg * 8;
+        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-      for(int s = 0; s < 4; s++) {
-        const int e = tid + s * DTHREADS;
-        y[s] = 0.0;
-        if(e < below * 16) {
-          const int r = c0 + 16 + e % below, c = e / below;
-          double ac[4] = {0.0, 0.0, 0.0, 0.0};
+        for(int kk = 0; kk < 4; kk++) {
+          const double af = S.D[(c0 + 4 * kk + t4) * DSB + r0 + gq];
 #pragma unroll
-          for(int q = 0; q < 16; q++)
-            if(q <= c) ac[q & 3] += S.D[(c0 + q) * DSB + r] * inv[c * 17 + q];
-          y[s] = (ac[0] + ac[1]) + (ac[2] + ac[3]);
-          if(LDL) y[s] *= S.rdv[c0 + c];
+          for(int nt = 0; nt < 2; nt++) dmma884(acc[nt][0], acc[nt][1], af, inv[(nt * 8 + gq) * 17 + 4 * kk + t4]);
         }
-      }
-      __syncthreads();
+        __syncwarp();
 #pragma unroll
-      for(int s = 0; s < 4; s++) {
-        const int e = tid + s * DTHREADS;
-        if(e < below * 16) S.D[(c0 + e / below) * DSB + c0 + 16 + e % below] = y[s];
+        for(int nt = 0; nt < 2; nt++)
+#pragma unroll
+          for(int h = 0; h < 2; h++) {
+            const int c = nt * 8 + 2 * t4 + h;
+            double v = acc[nt][h];
+            if(LDL) v *= S.rdv[c0 + c];
+            S.D[(c0 + c) * DSB + r0 + gq] = v;
+          }
       }
     }
     __syncthreads();
+    QP(2);
     {
-      const int hb2 = below / 2;
-      for(int e = tid; e < hb2 * hb2; e += DTHREADS) {
-        const int tc = e / hb2, ti = e % hb2;
-        if(ti < tc) continue;
-        const int c = c0 + 16 + 2 * tc, i = c0 + 16 + 2 * ti;
-        double s00 = 0.0, s01 = 0.0, s10 = 0.0, s11 = 0.0;
+      // rank-16 update of the remaining lower triangle, 8 x 8 tiles dealt to the warps
+      const int nt8 = below / 8;
+      const int ntiles = nt8 * (nt8 + 1) / 2;
+      for(int t = warp; t < ntiles; t += DTHREADS / 32) {
+        int ti = 0, rem = t;
+        while(rem > ti) { rem -= ti + 1; ti++; }
+        const int i0 = c0 + 16 + 8 * ti, j0 = c0 + 16 + 8 * rem;
+        double u0 = 0.0, u1 = 0.0;
 #pragma unroll
-        for(int p = 0; p < 16; p++) {
-          const double li0 = S.D[(c0 + p) * DSB + i], li1 = S.D[(c0 + p) * DSB + i + 1];
-          double lc0 = S.D[(c0 + p) * DSB + c], lc1 = S.D[(c0 + p) * DSB + c + 1];
-          if(LDL) { const double dp = S.dv[c0 + p]; lc0 *= dp; lc1 *= dp; }
-          s00 += li0 * lc0; s10 += li1 * lc0; s01 += li0 * lc1; s11 += li1 * lc1;
+        for(int kk = 0; kk < 4; kk++) {
+          const double af = S.D[(c0 + 4 * kk + t4) * DSB + i0 + gq];
+          double bf = S.D[(c0 + 4 * kk + t4) * DSB + j0 + gq];
+          if(LDL) bf *= S.dv[c0 + 4 * kk + t4];
+          dmma884(u0, u1, af, bf);
         }
-        S.D[c * DSB + i] -= s00;
-        S.D[c * DSB + i + 1] -= s10;
-        S.D[(c + 1) * DSB + i + 1] -= s11;
-        if(ti > tc) S.D[(c + 1) * DSB + i] -= s01;
+        const int i = i0 + gq, j = j0 + 2 * t4;
+        if(i >= j) S.D[j * DSB + i] -= u0;
+        if(i >= j + 1) S.D[(j + 1) * DSB + i] -= u1;
       }
     }
     __syncthreads();
+    QP(3);
   }
+#undef QP
 }
 
 // Off-diagonal 16 x 16 blocks of the 128 x 128 inverse from the factor (lower slots of S.D) and the 16 x 16 diagonal inverses:
-// block row a: Inv_ab = -Inv_aa * sum_{q=b}^{a-1} L_aq Inv_qb.
-__device__ void invert_block128(DiagSmem& S)
+// block row a: Inv_ab = -Inv_aa * sum_{q=b}^{a-1} L_aq Inv_qb -- two small DMMA products per block row.
+__device__ void invert_block128(DiagSmem& S, double* __restrict__ InvG)
 {
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int gq = lane >> 2, t4 = lane & 3;
   for(int a = 1; a < BB / 16; a++) {
     const int ncol = 16 * a;
-    for(int e = tid; e < 16 * ncol; e += blockDim.x) {
-      const int r = e & 15, c = e >> 4;
-      const int ra = ncol + r;
-      double acc = S.D[c * DSB + ra] * S.idg[c];
-      for(int q = c + 1; q < ncol; q++) acc += S.D[q * DSB + ra] * S.D[q * DSB + c];
-      S.Tt[c * 17 + r] = acc;
+    for(int t = warp; t < 4 * a; t += nwarps) { // T (16 x ncol) = L_a * InvLower: tile (rt, ct)
+      const int rt = t & 1, n0 = (t >> 1) * 8;
+      double u0 = 0.0, u1 = 0.0;
+      for(int q0 = n0; q0 < ncol; q0 += 4) {
+        const int q = q0 + t4, c = n0 + gq;
+        const double af = S.D[q * DSB + ncol + 8 * rt + gq];
+        const double bf = q > c ? S.D[q * DSB + c] : (q == c ? S.idg[c] : 0.0);
+        dmma884(u0, u1, af, bf);
+      }
+      S.Tt[(8 * rt + gq) * TLD + n0 + 2 * t4] = u0;
+      S.Tt[(8 * rt + gq) * TLD + n0 + 2 * t4 + 1] = u1;
     }
     __syncthreads();
     const double* inv = S.Inv16 + a * 16 * 17;
-    for(int e = tid; e < 16 * ncol; e += blockDim.x) {
-      const int r = e & 15, c = e >> 4;
-      double acc = 0.0;
+    for(int t = warp; t < 4 * a; t += nwarps) { // Inv_a,: = -Inv16_a * T
+      const int rt = t & 1, n0 = (t >> 1) * 8;
+      double u0 = 0.0, u1 = 0.0;
 #pragma unroll
-      for(int q = 0; q < 16; q++)
-        if(q <= r) acc += inv[r * 17 + q] * S.Tt[c * 17 + q];
-      S.D[(ncol + r) * DSB + c] = -acc;
+      for(int k4 = 0; k4 < 16; k4 += 4) dmma884(u0, u1, inv[(8 * rt + gq) * 17 + k4 + t4], S.Tt[(k4 + t4) * TLD + n0 + gq]);
+      const int ra = ncol + 8 * rt + gq, c = n0 + 2 * t4;
+      S.D[ra * DSB + c] = -u0;
+      S.D[ra * DSB + c + 1] = -u1;
+      InvG[(size_t)c * BB + ra] = -u0;
+      InvG[(size_t)(c + 1) * BB + ra] = -u1;
     }
     __syncthreads();
-  }
-}
-
-__device__ void store_inverse128(const DiagSmem& S, double* __restrict__ InvG)
-{
-  for(int e = threadIdx.x; e < BB * BB; e += blockDim.x) {
-    const int r = e % BB, c = e / BB;
-    InvG[e] = r > c ? S.D[r * DSB + c] : (r == c ? S.idg[r] : 0.0);
   }
 }
 
 template <bool LDL>
 __global__ void __launch_bounds__(DTHREADS, 1)
-k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restrict__ InvG, double* __restrict__ dinvG, int* __restrict__ info)
+k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restrict__ InvG, double* __restrict__ dinvG, int* __restrict__ info,
+          long long* __restrict__ prof /* NULL, or 8 cycle counters of thread 0: load, 16x16 factor+inverse, rows below, rank-16 update, store, inversion */)
 {
+  long long t0 = prof ? clock64() : 0;
+#define DP(slot) if(prof && threadIdx.x == 0) { const long long t1 = clock64(); prof[slot] += t1 - t0; t0 = t1; }
   extern __shared__ __align__(16) unsigned char dsm_raw[];
   DiagSmem& S = *reinterpret_cast<DiagSmem*>(dsm_raw);
   const int tid = threadIdx.x;
@@ -428,14 +447,18 @@ k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restri
     S.D[j * DSB + i] = v;
   }
   __syncthreads();
-  factor_block128<LDL>(S, k0, info);
+  DP(0);
+  factor_block128<LDL>(S, k0, info, InvG, prof);
+  if(prof) t0 = clock64();
   for(int e = tid; e < nb * nb; e += DTHREADS) {
     const int j = e / nb, i = e % nb;
     if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DSB + i];
   }
   if(LDL && tid < BB) dinvG[tid] = S.rdv[tid];
-  invert_block128(S);
-  store_inverse128(S, InvG);
+  DP(4);
+  invert_block128(S, InvG);
+  DP(5);
+#undef DP
 }
 
 // Inverses of the 128 x 128 diagonal triangles of an EXISTING factor (paths that do not run k_diag128: cooperative Cholesky,
@@ -448,12 +471,12 @@ k_block_inverses(const double* __restrict__ F, long long ldf, int N, int unit, d
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k0 = blockIdx.x * BB;
   const int nb = min(BB, N - k0);
+  double* InvG = InvAll + (size_t)blockIdx.x * BB * BB;
   for(int e = tid; e < BB * BB; e += DTHREADS) {
     const int j = e / BB, i = e % BB;
     double v = 0.0;
     if(i < nb && j < nb && i > j) v = LC(F, ldf, k0 + i, k0 + j);
     if(i == j) v = (i < nb && !unit) ? LC(F, ldf, k0 + i, k0 + i) : 1.0;
-    if(i < j) v = 0.0;
     S.D[j * DSB + i] = v;
   }
   __syncthreads();
@@ -480,18 +503,18 @@ k_block_inverses(const double* __restrict__ F, long long ldf, int N, int unit, d
       for(int r = 0; r < 16; r++) {
         inv[r * 17 + lane] = x[r];
         if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r];
+        if(r >= lane) InvG[(size_t)(c0 + lane) * BB + c0 + r] = x[r];
       }
     }
   }
   __syncthreads();
-  invert_block128(S);
-  store_inverse128(S, InvAll + (size_t)blockIdx.x * BB * BB);
+  invert_block128(S, InvG);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
 // Blocked solves. SB rows per launch; the stored inverses make the in-block solves matrix-vector products.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SB = 256;
+constexpr int SB = 128; // rows per step = one stored inverse
 constexpr int ST = 1024;
 
 struct StepSmem
@@ -499,47 +522,45 @@ struct StepSmem
   double xs[64];
   double red[ST];
   double y[SB];
-  double xo[SB];
-  int last;
 };
 
-// sub-block products of the last CTA. y (S.y) holds b - (outside contributions); on exit S.xo holds the solution of the step.
-__device__ void fwd_tail(StepSmem& S, const double* __restrict__ F, long long ldf, int k0, int nrows, const double* __restrict__ InvAll)
+// Every step is one launch of G + 1 CTAs. CTAs 1..G compute the partial products against the part of the vector that is already
+// solved; CTA 0 (the "tail") first pulls the 128 x 128 inverse of its block into REGISTERS (those loads do not depend on the
+// partials, so their latency overlaps the main phase), then waits for the ticket counter, adds the partials in a fixed order and
+// finishes the step with register / shared-memory products only. (A first version let the LAST main CTA do the tail of a 256-row
+// step: ~20 us per step of dependent L2 round trips, 1.7 ms per solve at N = 8192.)
+__device__ __forceinline__ void wait_counter(int* counter, int G)
 {
-  const int tid = threadIdx.x;
-  const int nsub = (nrows + BB - 1) / BB;
-  const int r = tid & 127, gsel = tid >> 7; // 8 groups
-  for(int s = 0; s < nsub; s++) {
-    const int rows = min(BB, nrows - s * BB);
-    if(s > 0) { // y_s -= L(s, 0:s) x_(0:s)
-      const int ncols = s * BB;
-      double acc = 0.0;
-      if(r < rows)
-        for(int j = gsel; j < ncols; j += 8) acc += LC(F, ldf, k0 + s * BB + r, k0 + j) * S.xo[j];
-      S.red[tid] = acc;
-      __syncthreads();
-      if(tid < rows) {
-        double t = 0.0;
-#pragma unroll
-        for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
-        S.y[s * BB + tid] -= t;
-      }
-      __syncthreads();
-    }
-    // x_s = Inv_s y_s  (Inv(r,c) at c*128 + r, lower triangular)
-    const double* Inv = InvAll + (size_t)(k0 / BB + s) * BB * BB;
-    double acc = 0.0;
-    for(int cc = gsel; cc <= r; cc += 8) acc += Inv[cc * BB + r] * S.y[s * BB + cc];
-    S.red[tid] = acc;
-    __syncthreads();
-    if(tid < BB) {
-      double t = 0.0;
-#pragma unroll
-      for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
-      S.xo[s * BB + tid] = t;
-    }
-    __syncthreads();
+  if(threadIdx.x == 0) {
+    volatile int* vc = counter;
+    while(*vc < G) __nanosleep(40);
+    __threadfence();
   }
+  __syncthreads();
+}
+
+// y[0..127] = xk - sum of the G partial vectors (fixed order); 1024 threads = 128 rows x 8 groups
+__device__ __forceinline__ void gather_partials(StepSmem& S, const double* __restrict__ partial, int G, int nrows, double xk_own)
+{
+  const int tid = threadIdx.x, r = tid & 127, gsel = tid >> 7;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int c = gsel;
+  for(; c + 24 < G; c += 32) {
+    a0 += __ldcg(&partial[(size_t)c * SB + r]);
+    a1 += __ldcg(&partial[(size_t)(c + 8) * SB + r]);
+    a2 += __ldcg(&partial[(size_t)(c + 16) * SB + r]);
+    a3 += __ldcg(&partial[(size_t)(c + 24) * SB + r]);
+  }
+  for(; c < G; c += 8) a0 += __ldcg(&partial[(size_t)c * SB + r]);
+  S.red[tid] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if(tid < SB) {
+    double t = 0.0;
+#pragma unroll
+    for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
+    S.y[tid] = tid < nrows ? xk_own - t : 0.0;
+  }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(ST, 1)
@@ -547,45 +568,59 @@ k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
                  double* __restrict__ partial, int* __restrict__ counter)
 {
   __shared__ StepSmem S;
-  const int tid = threadIdx.x, G = gridDim.x, b = blockIdx.x;
+  const int tid = threadIdx.x, G = gridDim.x - 1;
   const int nrows = min(SB, N - k0);
-  const int r = tid & 255, gsel = tid >> 8; // 4 column groups of 16
-  if(k0 > 0) {
+  const int r = tid & 127, gsel = tid >> 7; // 8 groups
+  if(blockIdx.x != 0) {
+    // ---- main: partial[b][r] = sum_{j in 64-column chunk b} L(k0 + r, j) x_j ----
+    const int b = blockIdx.x - 1;
     const int jb = b * 64;
     if(tid < 64) S.xs[tid] = (jb + tid < k0) ? x[jb + tid] : 0.0;
-    __syncthreads();
-    double acc = 0.0;
-    if(r < nrows) {
-      double v[16];
+    double v[8];
 #pragma unroll
-      for(int q = 0; q < 16; q++) {
-        const int j = jb + gsel * 16 + q;
-        v[q] = j < k0 ? LC(F, ldf, k0 + r, j) : 0.0;
-      }
-#pragma unroll
-      for(int q = 0; q < 16; q++) acc += v[q] * S.xs[gsel * 16 + q];
+    for(int q = 0; q < 8; q++) {
+      const int j = jb + gsel * 8 + q;
+      v[q] = (r < nrows && j < k0) ? LC(F, ldf, k0 + r, j) : 0.0;
     }
-    S.red[tid] = acc;
     __syncthreads();
-    if(tid < SB) partial[(size_t)b * SB + tid] = (S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid]);
-  }
-  __threadfence();
-  __syncthreads();
-  if(tid == 0) S.last = (atomicAdd(counter, 1) == G - 1);
-  __syncthreads();
-  if(!S.last) return;
-  __threadfence();
-  {
     double acc = 0.0;
-    if(k0 > 0 && r < nrows)
-      for(int c = gsel; c < G; c += 4) acc += __ldcg(&partial[(size_t)c * SB + r]);
+#pragma unroll
+    for(int q = 0; q < 8; q++) acc += v[q] * S.xs[gsel * 8 + q];
     S.red[tid] = acc;
     __syncthreads();
-    if(tid < SB) S.y[tid] = tid < nrows ? x[k0 + tid] - ((S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid])) : 0.0;
+    if(tid < SB) {
+      double t = 0.0;
+#pragma unroll
+      for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
+      partial[(size_t)b * SB + tid] = t;
+    }
+    __threadfence();
     __syncthreads();
+    if(tid == 0) atomicAdd(counter, 1);
+    return;
   }
-  fwd_tail(S, F, ldf, k0, nrows, InvAll);
-  if(tid < nrows) x[k0 + tid] = S.xo[tid];
+  // ---- tail CTA: x_k = Inv_k (b_k - partials); thread (r, gsel) holds Inv(r, gsel + 8 q) ----
+  const double* Inv = InvAll + (size_t)(k0 / BB) * BB * BB;
+  double inv[16];
+#pragma unroll
+  for(int q = 0; q < 16; q++) {
+    const int cc = gsel + 8 * q;
+    inv[q] = cc <= r ? Inv[cc * BB + r] : 0.0;
+  }
+  const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
+  wait_counter(counter, G);
+  gather_partials(S, partial, G, nrows, xk);
+  double acc = 0.0;
+#pragma unroll
+  for(int q = 0; q < 16; q++) acc += inv[q] * S.y[gsel + 8 * q];
+  S.red[tid] = acc;
+  __syncthreads();
+  if(tid < nrows) {
+    double t = 0.0;
+#pragma unroll
+    for(int q = 0; q < 8; q++) t += S.red[q * 128 + tid];
+    x[k0 + tid] = t;
+  }
   if(tid == 0) *counter = 0;
 }
 
@@ -595,96 +630,67 @@ k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
                  double* __restrict__ partial, int* __restrict__ counter)
 {
   __shared__ StepSmem S;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x - 1;
   const int nrows = min(SB, N - k0);
   const int k1 = k0 + nrows;
-  if(k1 < N) {
-    const int il = tid & 63, cg = tid >> 6; // 64 rows x 16 column groups of 16
+  if(blockIdx.x != 0) {
+    // ---- main: partial[b][j] = sum_{i in 64-row chunk b below the step} L(i, k0 + j) x_i ----
+    const int b = blockIdx.x - 1;
+    const int il = tid & 63, cg = tid >> 6; // 64 rows x 16 column groups of 8
     const int i = k1 + b * 64 + il;
     const double xi = i < N ? x[i] : 0.0;
-    double v[16];
+    double v[8];
 #pragma unroll
-    for(int q = 0; q < 16; q++) {
-      const int jl = cg * 16 + q;
-      v[q] = (i < N && jl < nrows) ? LC(F, ldf, i, k0 + jl) * xi : 0.0;
+    for(int q = 0; q < 8; q++) {
+      const int jl = cg * 8 + q;
+      v[q] = (i < N && jl < nrows) ? LC(F, ldf, i, k0 + jl) : 0.0;
     }
 #pragma unroll
-    for(int q = 0; q < 16; q++) v[q] = hb_warp_sum(v[q]);
+    for(int q = 0; q < 8; q++) v[q] = hb_warp_sum(v[q] * xi);
     if(lane == 0) {
 #pragma unroll
-      for(int q = 0; q < 16; q++) S.red[warp * 16 + q] = v[q];
+      for(int q = 0; q < 8; q++) S.red[warp * 8 + q] = v[q];
     }
     __syncthreads();
-    if(tid < SB) { // column tid: group tid/16 -> warps 2*(tid/16), 2*(tid/16)+1
-      const int cgi = tid >> 4, q = tid & 15;
-      partial[(size_t)b * SB + tid] = S.red[(2 * cgi) * 16 + q] + S.red[(2 * cgi + 1) * 16 + q];
+    if(tid < SB) { // column tid: group tid/8 -> warps 2*(tid/8), 2*(tid/8)+1
+      const int cgi = tid >> 3, q = tid & 7;
+      partial[(size_t)b * SB + tid] = S.red[(2 * cgi) * 8 + q] + S.red[(2 * cgi + 1) * 8 + q];
     }
+    __threadfence();
+    __syncthreads();
+    if(tid == 0) atomicAdd(counter, 1);
+    return;
   }
-  __threadfence();
-  __syncthreads();
-  if(tid == 0) S.last = (atomicAdd(counter, 1) == G - 1);
-  __syncthreads();
-  if(!S.last) return;
-  __threadfence();
-  {
-    const int r = tid & 255, gsel = tid >> 8;
+  // ---- tail CTA: x_k = Inv_k^T y; warp w owns columns w + 32 t (t < 4), lane owns rows lane + 32 u (u < 4) ----
+  const double* Inv = InvAll + (size_t)(k0 / BB) * BB * BB;
+  double it[16];
+#pragma unroll
+  for(int t = 0; t < 4; t++)
+#pragma unroll
+    for(int u = 0; u < 4; u++) {
+      const int cc = warp + 32 * t, rr = lane + 32 * u;
+      it[t * 4 + u] = rr >= cc ? Inv[cc * BB + rr] : 0.0;
+    }
+  const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
+  wait_counter(counter, G);
+  gather_partials(S, partial, G, nrows, xk);
+#pragma unroll
+  for(int t = 0; t < 4; t++) {
     double acc = 0.0;
-    if(k1 < N && r < nrows)
-      for(int c = gsel; c < G; c += 4) acc += __ldcg(&partial[(size_t)c * SB + r]);
-    S.red[tid] = acc;
-    __syncthreads();
-    if(tid < SB) S.y[tid] = tid < nrows ? x[k0 + tid] - ((S.red[tid] + S.red[256 + tid]) + (S.red[512 + tid] + S.red[768 + tid])) : 0.0;
-    __syncthreads();
+#pragma unroll
+    for(int u = 0; u < 4; u++) acc += it[t * 4 + u] * S.y[lane + 32 * u];
+    acc = hb_warp_sum(acc);
+    const int cc = warp + 32 * t;
+    if(lane == 0 && cc < nrows) x[k0 + cc] = acc;
   }
-  const int nsub = (nrows + BB - 1) / BB;
-  for(int s = nsub - 1; s >= 0; s--) {
-    const int cols = min(BB, nrows - s * BB);
-    // y_s -= L(t, s)^T x_t for the sub-blocks t > s of this step; then x_s = Inv_s^T y_s. One warp per column (4 columns per warp).
-    for(int cc = warp; cc < cols; cc += ST / 32) {
-      const int jl = s * BB + cc;
-      double acc = 0.0;
-      for(int il2 = (s + 1) * BB + lane; il2 < nrows; il2 += 32) acc += LC(F, ldf, k0 + il2, k0 + jl) * S.xo[il2];
-      acc = hb_warp_sum(acc);
-      if(lane == 0) S.y[jl] -= acc;
-    }
-    __syncthreads();
-    const double* Inv = InvAll + (size_t)(k0 / BB + s) * BB * BB;
-    for(int cc = warp; cc < BB; cc += ST / 32) {
-      double acc = 0.0;
-      for(int rr = cc + lane; rr < BB; rr += 32) acc += Inv[cc * BB + rr] * S.y[s * BB + rr];
-      acc = hb_warp_sum(acc);
-      if(lane == 0) S.xo[s * BB + cc] = acc;
-    }
-    __syncthreads();
-  }
-  if(tid < nrows) x[k0 + tid] = S.xo[tid];
   if(tid == 0) *counter = 0;
 }
 
-// block-diagonal solve between the sweeps: LDL^T without pivoting (ipiv == NULL: 1x1 blocks) or Bunch-Kaufman (2x2 blocks flagged
-// by ipiv[k] < 0 on both rows, LAPACK convention; the sub-diagonal entry of the block is F(k+1,k))
-__global__ void k_dsolve(const double* __restrict__ F, long long ldf, int N, const int* __restrict__ ipiv, double* __restrict__ x)
+// diagonal solve between the sweeps of the no-pivot LDL^T (the Bunch-Kaufman block diagonal lives in hb_bk_cluster.cu)
+__global__ void k_dsolve(const double* __restrict__ F, long long ldf, int N, double* __restrict__ x)
 {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if(k >= N) return;
-  if(!ipiv || ipiv[k] > 0) {
-    x[k] = x[k] / LC(F, ldf, k, k);
-    return;
-  }
-  // 2x2 block: handled by its first row
-  if(k > 0 && ipiv[k - 1] < 0) {
-    // is k the second row of a block? count the run of negatives ending at k-1
-    int run = 0;
-    for(int q = k - 1; q >= 0 && ipiv[q] < 0; q--) run++;
-    if(run & 1) return;
-  }
-  const double akm1k = LC(F, ldf, k + 1, k);
-  const double akm1 = LC(F, ldf, k, k) / akm1k;
-  const double ak = LC(F, ldf, k + 1, k + 1) / akm1k;
-  const double denom = akm1 * ak - 1.0;
-  const double bkm1 = x[k] / akm1k, bk = x[k + 1] / akm1k;
-  x[k] = (ak * bkm1 - bk) / denom;
-  x[k + 1] = (akm1 * bk - bkm1) / denom;
+  if(k < N) x[k] = x[k] / LC(F, ldf, k, k);
 }
 
 __global__ void k_gather(int N, const int* __restrict__ perm, const double* __restrict__ in, double* __restrict__ out)
@@ -759,6 +765,7 @@ int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w)
       cudaGetLastError();
       return hb_fail(HB_ERR_ALLOC, "hb_big_reserve: scratch allocation failed%s", "");
     }
+    HB_CUDA(cudaMemsetAsync(b->InvAll, 0, sizeof(double) * (size_t)nblk * BB * BB, c->stream)); // the kernels only write the lower triangles
     if(!b->dinv) HB_CUDA(cudaMalloc(&b->dinv, sizeof(double) * BB));
     if(!b->counter) {
       HB_CUDA(cudaMalloc(&b->counter, sizeof(int) * 4));
@@ -793,8 +800,8 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
     double* Wb = ldl ? b->W[blk & 1] : nullptr;
     // ---- panel stream: diagonal block, then L21 ----
     HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd, 0));
-    if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev);
-    else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev);
+    if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev, nullptr);
+    else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev, nullptr);
     HB_LAUNCHED();
     if(r0 < N) {
       GemmArgs g{};
@@ -836,6 +843,25 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
   return HB_OK;
 }
 
+// diagnostics: cycle counters of the phases of one k_diag128 launch on the block at k0 (the matrix is modified like in the factorization)
+int hb_big_diag_profile(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int k0, bool ldl, long long* prof_host8)
+{
+  HB_CHECK(hb_big_reserve(c, b, N, false));
+  long long* prof = nullptr;
+  HB_CUDA(cudaMalloc(&prof, sizeof(long long) * 8));
+  HB_CUDA(cudaMemsetAsync(prof, 0, sizeof(long long) * 8, c->stream));
+  int* info = nullptr;
+  HB_CUDA(cudaMalloc(&info, sizeof(int)));
+  HB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), c->stream));
+  if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->InvAll, b->dinv, info, prof);
+  else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->InvAll, b->dinv, info, prof);
+  HB_LAUNCHED();
+  HB_CUDA(cudaMemcpyAsync(prof_host8, prof, sizeof(long long) * 8, cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  cudaFree(prof); cudaFree(info);
+  return HB_OK;
+}
+
 // trailing update of a pivoted panel whose origin / width live in device memory (state[0] = k0, state[1] = kb): A22 -= W21 L21^T
 int hb_big_trailing_from_state(hb_ctx* c, int N, double* A, long long lda, const double* W, long long ldw, const int* state_dev, int r0_min, cudaStream_t st)
 {
@@ -846,7 +872,8 @@ int hb_big_trailing_from_state(hb_ctx* c, int N, double* A, long long lda, const
   g.C = A; g.ldc = lda;
   g.i_base = g.j_base = r0_min; g.i_end = N; g.j_end = N; g.tj0 = 0;
   g.state = state_dev;
-  const int nti = (N - r0_min + TM - 1) / TM, ntj = (N - r0_min + 63) / 64;
+  const int org = r0_min & ~1; // the kernel rounds its tile origin down to an even row
+  const int nti = (N - org + TM - 1) / TM, ntj = (N - org + 63) / 64;
   k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj), 256, GemmCfg<64>::SMEM, st>>>(g);
   HB_LAUNCHED();
   return HB_OK;
@@ -865,8 +892,10 @@ int hb_big_block_inverses(hb_ctx* c, hb_big* b, int N, const double* F, long lon
 }
 
 // x <- solution of (L [D] L^T) x = x with the factor F (+ b->InvAll). dmode: 0 = Cholesky (no D), 1 = D from the diagonal (LDL^T),
-// 2 = Bunch-Kaufman block diagonal (ipiv_dev), perm_dev (may be NULL): x is gathered through it first and scattered back at the end.
-int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const int* perm_dev, double* x)
+// 2 = Bunch-Kaufman block diagonal (ipiv_dev, dsub_dev), perm_dev (may be NULL): x is gathered through it first and scattered back at the end.
+int hb_bkc_dsolve(hb_ctx* c, int N, const double* F, long long ldf, const int* ipiv_dev, const double* dsub_dev, double* x);
+int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, int dmode, const int* ipiv_dev, const double* dsub_dev, const int* perm_dev,
+                 double* x)
 {
   HB_REQUIRE(b->inv_valid && b->capN >= N, "hb_big_solve: no block inverses for this factor");
   if(N == 0) return HB_OK;
@@ -878,20 +907,22 @@ int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, in
     v = b->xtmp;
   }
   for(int k0 = 0; k0 < N; k0 += SB) {
-    const int G = k0 > 0 ? (k0 + 63) / 64 : 1;
-    k_solve_fwd_step<<<G, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    const int G = (k0 + 63) / 64;
+    k_solve_fwd_step<<<G + 1, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
     HB_LAUNCHED();
   }
-  if(dmode != 0) {
-    k_dsolve<<<(N + 127) / 128, 128, 0, st>>>(F, ldf, N, dmode == 2 ? ipiv_dev : nullptr, v);
+  if(dmode == 1) {
+    k_dsolve<<<(N + 127) / 128, 128, 0, st>>>(F, ldf, N, v);
     HB_LAUNCHED();
+  } else if(dmode == 2) {
+    HB_CHECK(hb_bkc_dsolve(c, N, F, ldf, ipiv_dev, dsub_dev, v));
   }
   const int last = ((N - 1) / SB) * SB;
   for(int k0 = last; k0 >= 0; k0 -= SB) {
     const int nrows = N - k0 < SB ? N - k0 : SB;
     const int below = N - (k0 + nrows);
-    const int G = below > 0 ? (below + 63) / 64 : 1;
-    k_solve_bwd_step<<<G, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    const int G = (below + 63) / 64;
+    k_solve_bwd_step<<<G + 1, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
     HB_LAUNCHED();
   }
   if(perm_dev) {

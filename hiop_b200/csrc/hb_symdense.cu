@@ -17,6 +17,13 @@ struct hb_symdense
   long long ldf = 0;
   hb_big big;               // large-N path: streams, diagonal-block inverses, solve scratch
   bool big_solve = false;   // the current factor is solved with hb_big_solve
+  // cluster Bunch-Kaufman (hb_bk_cluster.cu): permuted factor P A P^T = L D L^T
+  bool bkc = false;
+  double* dsub = nullptr;   // sub-diagonal of the 2x2 blocks of D
+  int* perm = nullptr;      // gather order of the right-hand side
+  int* bk_state = nullptr;  // device: k0, kb, info, -
+  int* swaplog = nullptr;
+  double* Wp = nullptr;     // W = L*D of the current panel
   int* ipiv = nullptr;
   int* info = nullptr;      // device: [0] info, [1..3] inertia
   int* info_host = nullptr; // pinned
@@ -36,6 +43,12 @@ int big_factor_min(int mode)
   return mode == HB_FACT_CHOLESKY ? 1025 : 257;
 }
 constexpr int BIG_SOLVE_MIN_N = 257;
+// Bunch-Kaufman: from this N on the cluster panel kernel factors (below: one-CTA DLASYF panels / DSYTF2). HB_BK_CLUSTER_MIN overrides.
+int bk_cluster_min()
+{
+  static const int env = getenv("HB_BK_CLUSTER_MIN") ? atoi(getenv("HB_BK_CLUSTER_MIN")) : -1;
+  return env >= 0 ? env : 385;
+}
 }
 
 extern "C" int hb_symdense_create(hb_ctx* c, int N, hb_symdense** out)
@@ -64,6 +77,7 @@ extern "C" int hb_symdense_destroy(hb_symdense* s)
   cudaSetDevice(s->ctx->device);
   cudaStreamSynchronize(s->ctx->stream);
   hb_big_release(&s->big);
+  cudaFree(s->dsub); cudaFree(s->perm); cudaFree(s->bk_state); cudaFree(s->swaplog); cudaFree(s->Wp);
   cudaFree(s->M); cudaFree(s->W); cudaFree(s->xbuf); cudaFree(s->ipiv); cudaFree(s->info); cudaFree(s->Fpad);
   cudaFreeHost(s->info_host);
   delete s;
@@ -82,10 +96,11 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
   s->factored = false;
   if(N == 0) { s->factored = true; s->n_neg = s->n_null = s->n_pos = 0; return 0; }
   HB_CUDA(cudaMemsetAsync(s->info, 0, sizeof(int) * 4, c->stream));
-  s->F = s->M; s->ldf = N; s->big_solve = false; s->big.inv_valid = false;
-  const bool blocked_bk = (mode == HB_FACT_BUNCH_KAUFMAN && N >= BLOCKED_BK_MIN_N);
+  s->F = s->M; s->ldf = N; s->big_solve = false; s->big.inv_valid = false; s->bkc = false;
+  const bool bkc = (mode == HB_FACT_BUNCH_KAUFMAN && N >= bk_cluster_min() && hb_bkc_supported(c, N));
+  const bool blocked_bk = (mode == HB_FACT_BUNCH_KAUFMAN && !bkc && N >= BLOCKED_BK_MIN_N);
   const bool big = (mode != HB_FACT_BUNCH_KAUFMAN && N >= big_factor_min(mode));
-  if(big) {
+  if(big || bkc) {
     if(N & 1) { // even leading dimension for the 16-byte operand copies
       const long long ld = (N + 7) & ~7LL;
       if(!s->Fpad) {
@@ -95,7 +110,22 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
       HB_CUDA(cudaMemcpy2DAsync(s->Fpad, sizeof(double) * ld, s->M, sizeof(double) * N, sizeof(double) * N, N, cudaMemcpyDeviceToDevice, c->stream));
       s->F = s->Fpad; s->ldf = ld;
     }
-    HB_CHECK(hb_big_factor(c, &s->big, N, s->F, s->ldf, mode == HB_FACT_NOPIV, s->info));
+    if(big) {
+      HB_CHECK(hb_big_factor(c, &s->big, N, s->F, s->ldf, mode == HB_FACT_NOPIV, s->info));
+    } else {
+      const long long ldw = (N + 7) & ~7LL;
+      if(!s->dsub) {
+        if(cudaMalloc(&s->dsub, sizeof(double) * (N + 2)) != cudaSuccess || cudaMalloc(&s->perm, sizeof(int) * (N + 2)) != cudaSuccess ||
+           cudaMalloc(&s->bk_state, sizeof(int) * 4) != cudaSuccess || cudaMalloc(&s->swaplog, sizeof(int) * HB_BKC_SWAPLOG_INTS(N)) != cudaSuccess ||
+           cudaMalloc(&s->Wp, sizeof(double) * (size_t)ldw * 32) != cudaSuccess) {
+          cudaGetLastError();
+          return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate the Bunch-Kaufman scratch%s", "");
+        }
+      }
+      HB_CHECK(hb_bkc_factor(c, &s->big, N, s->F, s->ldf, s->ipiv, s->dsub, s->perm, s->Wp, ldw, s->bk_state, s->swaplog, s->info));
+      HB_CHECK(hb_big_block_inverses(c, &s->big, N, s->F, s->ldf, true));
+      s->bkc = true;
+    }
     s->big_solve = true;
   } else
   if((mode == HB_FACT_NOPIV || blocked_bk) && !s->W) {
@@ -104,7 +134,7 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
       return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate panel scratch%s", "");
     }
   }
-  if(big) {
+  if(big || bkc) {
   } else if(mode == HB_FACT_BUNCH_KAUFMAN) {
     if(blocked_bk) HB_CHECK(hb_dense_sytrf_blocked(c, N, s->M, N, s->ipiv, s->W, s->info));
     else HB_CHECK(hb_dense_sytf2(c, N, s->M, N, s->ipiv, s->info));
@@ -115,7 +145,9 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
       s->big_solve = true;
     }
   }
-  HB_CHECK(hb_dense_inertia(c, N, s->F, (int)s->ldf, s->ipiv, mode, s->info + 1));
+  if(bkc) HB_CHECK(hb_bkc_inertia(c, N, s->F, s->ldf, s->ipiv, s->dsub, s->info + 1));
+  else if(mode != HB_FACT_BUNCH_KAUFMAN) HB_CHECK(hb_bkc_inertia(c, N, s->F, s->ldf, nullptr, nullptr, s->info + 1)); // signs of the diagonal
+  else HB_CHECK(hb_dense_inertia(c, N, s->F, (int)s->ldf, s->ipiv, mode, s->info + 1));
   HB_CUDA(cudaMemcpyAsync(s->info_host, s->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   s->n_neg = s->info_host[1]; s->n_null = s->info_host[2]; s->n_pos = s->info_host[3];
@@ -143,7 +175,8 @@ extern "C" int hb_symdense_solve(hb_symdense* s, double* x, int nrhs)
   hb_ctx* c = s->ctx;
   if(s->big_solve) {
     for(int r = 0; r < nrhs; r++)
-      HB_CHECK(hb_big_solve(c, &s->big, s->N, s->F, s->ldf, s->mode == HB_FACT_CHOLESKY ? 0 : 1, nullptr, nullptr, x + (size_t)r * s->N));
+      HB_CHECK(hb_big_solve(c, &s->big, s->N, s->F, s->ldf, s->bkc ? 2 : (s->mode == HB_FACT_CHOLESKY ? 0 : 1), s->ipiv, s->dsub, s->bkc ? s->perm : nullptr,
+                            x + (size_t)r * s->N));
   } else if(s->mode == HB_FACT_BUNCH_KAUFMAN) {
     HB_CHECK(hb_dense_sytrs(c, s->N, s->M, s->N, s->ipiv, x, s->N, nrhs));
   } else {
@@ -177,4 +210,16 @@ extern "C" int hb_symdense_solve_host(hb_symdense* s, double* x_host, int nrhs)
   HB_CUDA(cudaMemcpyAsync(x_host, s->xbuf, sizeof(double) * need, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));
   return 1;
+}
+
+// diagnostics (tools/prof_diag.py): phase cycle counters of the 128 x 128 diagonal-block kernel on the leading block of M
+extern "C" int hb_debug_diag128_profile(hb_symdense* s, int ldl, long long* prof_host8)
+{
+  HB_REQUIRE(s && prof_host8 && s->N >= 128 && (s->N & 1) == 0, "hb_debug_diag128_profile: needs an even N >= 128");
+  return hb_big_diag_profile(s->ctx, &s->big, s->N, s->M, s->N, 0, ldl != 0, prof_host8);
+}
+extern "C" int hb_debug_bk_profile(hb_ctx* c, int on, long long* prof_host8)
+{
+  HB_REQUIRE(c, "null ctx");
+  return hb_bkc_profile(c, on, prof_host8);
 }

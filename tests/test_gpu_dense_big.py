@@ -77,3 +77,46 @@ def test_factor_is_reproducible(ctx):
     K = synth.make_kkt_like(900, 400, seed=8)
     outs = [_factor_solve(ctx, K, LinSolverSymDense.NOPIV, seed=1)[3] for _ in range(3)]
     assert np.array_equal(outs[0], outs[1]) and np.array_equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("N,nneg", [(400, 150), (513, 256), (1000, 333), (1537, 700)])
+def test_bunch_kaufman_cluster_general_indefinite(ctx, N, nneg):
+    """cluster panel kernel (hb_bk_cluster.cu): tiny diagonal -> 2x2 pivots and interchanges far outside the panel; the inertia must equal
+    the eigenvalue count (DSYTRF + the dsidi rule of hiopLinSolverSymDenseLapack.hpp:127-167) and the solve must match LAPACK's"""
+    from hiop_b200.engine import LinSolverSymDense
+    M = synth.make_symmetric_indefinite(N, nneg, seed=N)
+    M[np.diag_indices(N)] *= 1e-6
+    ev = np.linalg.eigvalsh(M)
+    ret, ok, rhs, xs = _factor_solve(ctx, M, LinSolverSymDense.BUNCH_KAUFMAN, nrhs=2, seed=N)
+    assert ret == int((ev < 0).sum()) and ok
+    ref = np.linalg.solve(M, rhs.T).T
+    assert np.abs(M @ xs.T - rhs.T).max() <= 1e-9 * np.abs(rhs).max() * max(1.0, np.linalg.cond(M) * 1e-3)
+    assert np.abs(xs - ref).max() <= 1e-7 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("nx,m", [(300, 100), (700, 324), (1500, 1001), (2200, 900)])
+def test_bunch_kaufman_cluster_kkt(ctx, nx, m):
+    from hiop_b200.engine import LinSolverSymDense
+    K = synth.make_kkt_like(nx, m, seed=nx + m)
+    ret, ok, rhs, xs = _factor_solve(ctx, K, LinSolverSymDense.BUNCH_KAUFMAN, nrhs=1, seed=m)
+    assert ret == m and ok
+    ref = np.linalg.solve(K, rhs.T).T
+    assert np.abs(xs - ref).max() <= 1e-8 * np.abs(ref).max()
+
+
+def test_bunch_kaufman_cluster_mixed_scales_and_singular(ctx):
+    from hiop_b200.engine import LinSolverSymDense
+    r = np.random.default_rng(11)
+    N = 900
+    A = r.standard_normal((N, N))
+    M = A + A.T
+    M[np.diag_indices(N)] *= r.choice([1e-3, 1.0, 10.0], N)
+    ev = np.linalg.eigvalsh(M)
+    ret, ok, rhs, xs = _factor_solve(ctx, M, LinSolverSymDense.BUNCH_KAUFMAN, seed=3)
+    assert ret == int((ev < 0).sum()) and ok
+    assert np.abs(M @ xs.T - rhs.T).max() <= 1e-8 * np.abs(rhs).max() * max(1.0, np.linalg.cond(M) * 1e-3)
+    K = synth.make_kkt_like(500, 120, seed=3)
+    K[3, :] = 0.0
+    K[:, 3] = 0.0
+    ret, ok, _, _ = _factor_solve(ctx, K, LinSolverSymDense.BUNCH_KAUFMAN)
+    assert ret == -1
