@@ -59,17 +59,56 @@ __device__ ArgMax cta_argmax(ArgMax a, ArgMax* sm)
   __syncthreads();
   if(lane == 0) sm[warp] = a;
   __syncthreads();
-  ArgMax r = sm[0];
-#pragma unroll 4
-  for(int w = 1; w < PT / 32; w++) r = am_comb(r, sm[w]);
+  // second stage by shuffles in every warp (a loop over the 32 partials in all 1024 threads cost ~2500 cycles of LDS traffic per column)
+  ArgMax r{-1.0, 0x7fffffff};
+  if(lane < (int)(blockDim.x >> 5)) r = sm[lane];
+#pragma unroll
+  for(int o = 16; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, r.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, r.i, o);
+    r = am_comb(r, b);
+  }
   return r;
+}
+// the 16 per-CTA candidates of a mailbox -> the cluster-wide maximum (every warp by shuffles)
+template <typename IT>
+__device__ __forceinline__ ArgMax mailbox_argmax(const double* v, const IT* idx)
+{
+  const int lane = threadIdx.x & 31;
+  ArgMax r{-1.0, 0x7fffffff};
+  if(lane < CS) { r.v = v[lane]; r.i = (int)idx[lane]; }
+#pragma unroll
+  for(int o = 8; o > 0; o >>= 1) {
+    ArgMax b;
+    b.v = __shfl_xor_sync(0xffffffffu, r.v, o);
+    b.i = __shfl_xor_sync(0xffffffffu, r.i, o);
+    r = am_comb(r, b);
+  }
+  r.v = __shfl_sync(0xffffffffu, r.v, 0);
+  r.i = __shfl_sync(0xffffffffu, r.i, 0);
+  return r;
+}
+
+__device__ __forceinline__ unsigned bk_s2u(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned bk_mapa(unsigned a, unsigned rank)
+{
+  unsigned r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  return r;
+}
+// 8 bytes to the same shared-memory location of CTA `rank`, completing 8 bytes of that CTA's mailbox barrier
+__device__ __forceinline__ void bk_post(const void* local_dst, unsigned long long bits, const void* local_bar, unsigned rank)
+{
+  const unsigned ra = bk_mapa(bk_s2u(local_dst), rank), rb = bk_mapa(bk_s2u(local_bar), rank);
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(ra), "l"(bits), "r"(rb) : "memory");
 }
 
 // replicated per-step mailbox (one per parity); every CTA of the cluster holds a copy that the others write through DSM
 struct BkStep
 {
   double cand_v[CS];
-  int cand_i[CS];
+  long long cand_i[CS];
   double coltop[NBMAX];      // column k at the panel's top rows: coltop[c] = T(k0+c, k), c >= kl                (from CTA 0, every step)
   double coltop1[NBMAX];     // column k+1 at the top rows, c >= kl+1                                            (from CTA 0, fail path)
   double colimax_top[NBMAX]; // column imax at the top rows below imax (imax inside the panel)                   (from CTA 0, fail path)
@@ -88,18 +127,22 @@ struct BkShared
   double d11[NBMAX], d21[NBMAX], d22[NBMAX];
   double ptop1[NBMAX], ptop2[NBMAX], ctop[NBMAX], vld[NBMAX];
   int swaps[2 * NBMAX];
+  unsigned long long mbar[2]; // per-parity mailbox barriers: the step's posts arrive as st.async ... complete_tx (no cluster barrier, no fence)
+  int piv[NBMAX];      // ipiv / dsub of the panel's columns, written to global memory once per panel (a global store per column sat in
+  double sub[NBMAX];   // front of every cluster barrier: its release fence waits for all outstanding stores)
 };
 
 // swap log of one panel (global): [0] = number of interchanges, [1] = k0, [2] = kb, then (kk, kp) pairs
 constexpr int SWAPLOG_STRIDE = 4 + 2 * NBMAX;
 
+template <bool PROF>
 __global__ void __cluster_dims__(CS, 1, 1) __launch_bounds__(PT, 1)
 k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W, long long ldw, int NB, int S, int* __restrict__ ipiv,
            double* __restrict__ dsub, int* __restrict__ state, int* __restrict__ swaplog_all, int panel_index,
            long long* __restrict__ prof /* NULL or 8 cycle counters (CTA 0, thread 0): load, column max, barrier 1, fail path, interchange, pivot, write-back */)
 {
-  long long pt0 = prof ? clock64() : 0;
-#define PP(slot) if(prof && threadIdx.x == 0 && rank == 0) { const long long pt1 = clock64(); prof[slot] += pt1 - pt0; pt0 = pt1; }
+  long long pt0 = PROF ? clock64() : 0;
+#define PP(slot) if(PROF && threadIdx.x == 0 && rank == 0) { const long long pt1 = clock64(); prof[slot] += pt1 - pt0; pt0 = pt1; }
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();
   extern __shared__ __align__(16) unsigned char bk_smem[];
@@ -107,7 +150,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
   double* ccol = slab + (size_t)NB * S;                       // [S] candidate column (own rows)
   BkStep* bc = reinterpret_cast<BkStep*>(ccol + S);           // [2]
   __shared__ BkShared sh;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
   int* swaplog = swaplog_all + (size_t)panel_index * SWAPLOG_STRIDE;
   const int k0 = state[0];
   if(k0 >= N) {
@@ -120,46 +163,66 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
   const int lo = k0 + rank * S;
   const int big = 0x7fffffff;
   // ---- load the slab (lower part of the panel columns; zeros elsewhere) ----
-  for(int c = 0; c < nbp; c++)
-    for(int rl = tid; rl < S; rl += PT) {
-      const int i = lo + rl;
-      slab[(size_t)c * S + rl] = (i < N && i >= k0 + c) ? LC(A, lda, i, k0 + c) : 0.0;
+  for(int rl = tid; rl < S; rl += nthr) {
+    const int i = lo + rl;
+    for(int c0 = 0; c0 < nbp; c0 += 8) { // 8 independent loads in flight per thread
+      double v[8];
+#pragma unroll
+      for(int q = 0; q < 8; q++) {
+        const int c = c0 + q;
+        v[q] = (c < nbp && i < N && i >= k0 + c) ? LC(A, lda, i, k0 + c) : 0.0;
+      }
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+        if(c0 + q < nbp) slab[(size_t)(c0 + q) * S + rl] = v[q];
     }
+  }
   if(tid < NBMAX) sh.dtype[tid] = 0;
+  if(tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_s2u(&sh.mbar[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bk_s2u(&sh.mbar[1])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
   cluster.sync();
   PP(0);
 
-  int k = k0, nsw = 0, linfo = 0, par = 0;
+  int k = k0, nsw = 0, linfo = 0, step = 0;
   while(k < N && (last || (k - k0) < NB - 1)) {
     const int kl = k - k0;
+    const int par = step & 1;
     BkStep* my = &bc[par];
-    par ^= 1;
+    unsigned long long* mb = &sh.mbar[par];
+    const unsigned mphase = (unsigned)((step >> 1) & 1); // each parity's barrier completes once every second step
+    step++;
     // ---- S1: column maximum over my rows i > k, posted to every CTA; CTA 0 posts the top of column k ----
     {
       ArgMax a{-1.0, big};
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         if(i < N && i > k) a = am_comb(a, ArgMax{fabs(slab[(size_t)kl * S + rl]), i});
       }
       a = cta_argmax(a, sh.am);
+      // this step's mail: 16 candidates (value + index) from the 16 CTAs and the top of column k from CTA 0
+      if(tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bk_s2u(mb)), "r"(CS * 16 + nbp * 8) : "memory");
       if(tid < CS) {
-        BkStep* r = cluster.map_shared_rank(my, tid);
-        r->cand_v[rank] = a.v;
-        r->cand_i[rank] = a.i;
+        bk_post(&my->cand_v[rank], (unsigned long long)__double_as_longlong(a.v), mb, tid);
+        bk_post(&my->cand_i[rank], (unsigned long long)(long long)a.i, mb, tid);
       }
       if(rank == 0)
-        for(int e = tid; e < CS * nbp; e += PT) {
+        for(int e = tid; e < CS * nbp; e += nthr) {
           const int dst = e / nbp, c = e % nbp;
-          if(c >= kl) cluster.map_shared_rank(my, dst)->coltop[c] = slab[(size_t)kl * S + c];
+          bk_post(&my->coltop[c], (unsigned long long)__double_as_longlong(slab[(size_t)kl * S + c]), mb, dst);
         }
     }
     PP(1);
-    cluster.sync();
+    {
+      unsigned ok = 0;
+      while(!ok)
+        asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2;\nselp.u32 %0, 1, 0, q;\n}" : "=r"(ok) : "r"(bk_s2u(mb)), "r"(mphase) : "memory");
+    }
     PP(2);
-    ArgMax cm{-1.0, big};
-#pragma unroll
-    for(int r = 0; r < CS; r++) cm = am_comb(cm, ArgMax{my->cand_v[r], my->cand_i[r]});
+    const ArgMax cm = mailbox_argmax(my->cand_v, my->cand_i);
     const double absakk = fabs(my->coltop[kl]);
     double colmax = 0.0;
     int imax = k;
@@ -177,12 +240,12 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
       const bool inpanel = il < nbp;
       // F1: owner posts row imax of the slab; CTA 0 posts rows k, k+1, the top of column k+1 and (inside the panel) of column imax
       if(rank == owner)
-        for(int e = tid; e < CS * nbp; e += PT) {
+        for(int e = tid; e < CS * nbp; e += nthr) {
           const int dst = e / nbp, c = e % nbp;
           cluster.map_shared_rank(my, dst)->rowimax[c] = slab[(size_t)c * S + (imax - lo)];
         }
       if(rank == 0)
-        for(int e = tid; e < CS * nbp; e += PT) {
+        for(int e = tid; e < CS * nbp; e += nthr) {
           const int dst = e / nbp, c = e % nbp;
           BkStep* r = cluster.map_shared_rank(my, dst);
           r->rowk[c] = slab[(size_t)c * S + kl];
@@ -205,7 +268,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
       __syncthreads();
       // F2: my part of the candidate column
       ArgMax a2{-1.0, big};
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         double cv = 0.0;
         if(i < N && i >= k) {
@@ -229,9 +292,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
         if(rank == owner) r->diag_imax = ccol[imax - lo];
       }
       cluster.sync();
-      double rowmax = 0.0;
-#pragma unroll
-      for(int r = 0; r < CS; r++) rowmax = fmax(rowmax, my->cand2_v[r]);
+      const double rowmax = fmax(0.0, mailbox_argmax(my->cand2_v, my->cand2_i).v);
       if(absakk >= BK_ALPHA * colmax * (colmax / rowmax)) kp = k;
       else if(fabs(my->diag_imax) >= BK_ALPHA * rowmax) kp = imax;
       else { kp = imax; kstep = 2; }
@@ -260,7 +321,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
       const double* oldtop_kk = (kk == k) ? my->coltop : my->coltop1;   // old column kk at the top rows
       const double* oldrow_kk = (kk == k) ? my->rowk : my->rowk1;
       // ---- global (non-updated) trailing matrix: DLASYF's copies of column kk into position kp (row owners only) ----
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         if(i < N) {
           if(i > kp) LC(A, lda, i, kp) = __ldcg(&LC(A, lda, i, kk));
@@ -270,7 +331,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
       }
       // ---- slab: column kp (inside the panel) takes the old column kk below kp ----
       if(kpl < nbp) {
-        for(int rl = tid; rl < S; rl += PT) {
+        for(int rl = tid; rl < S; rl += nthr) {
           const int i = lo + rl;
           if(i < N && i > kp) slab[(size_t)kpl * S + rl] = slab[(size_t)kkl * S + rl];
         }
@@ -285,7 +346,7 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
         else if(c > kkl && k0 + c < kp) slab[(size_t)c * S + (kp - lo)] = oldtop_kk[c];
       }
       // ---- slab: new column kk = candidate column with the entries at positions kk and kp exchanged ----
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         if(i < N && i >= kk) {
           double v = ccol[rl];
@@ -305,38 +366,51 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
     // =================== pivot ===================
     if(kstep == 1) {
       double d;
-      if(tid < NBMAX) { // pivot column at the top rows
-        const int c = tid;
-        double v = 0.0;
-        if(c < nbp) {
-          if(!have_cand || kp == k) v = my->coltop[c];
-          else { // interchange: candidate column with positions kkl and kpl exchanged
+      const bool plain = (!have_cand || kp == k); // the pivot column is column k as it stands: its top entries are in the mailbox
+      const double* ptop = my->coltop;
+      if(!plain) {
+        if(tid < NBMAX) { // interchange: candidate column with positions kkl and kpl exchanged
+          const int c = tid;
+          double v = 0.0;
+          if(c < nbp) {
             const int kpl = kp - k0;
             v = sh.ctop[c];
             if(c == kkl) v = my->diag_imax;
             else if(c == kpl) v = sh.ctop[kkl];
           }
+          sh.ptop1[c] = v;
         }
-        sh.ptop1[c] = v;
+        __syncthreads();
+        ptop = sh.ptop1;
       }
-      d = (!have_cand || kp == k) ? my->coltop[kl] : my->diag_imax;
-      __syncthreads();
+      d = plain ? my->coltop[kl] : my->diag_imax;
       const double r1 = 1.0 / d;
       if(tid == 0) { sh.dtype[kl] = 1; sh.d11[kl] = d; }
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         if(i < N && i > k && !zero_col) {
           const double w = slab[(size_t)kl * S + rl];
           const double l = w * r1;
           const int cend = min(nbp - 1, i - k0);
-          for(int c = kl + 1; c <= cend; c++) slab[(size_t)c * S + rl] -= l * sh.ptop1[c];
+          for(int c0 = kl + 1; c0 <= cend; c0 += 8) { // loads first, then the FMAs, then the stores (no dependent LDS/STS chain)
+            double v[8], pt[8];
+#pragma unroll
+            for(int q = 0; q < 8; q++) {
+              const int c = min(c0 + q, nbp - 1);
+              v[q] = slab[(size_t)c * S + rl];
+              pt[q] = ptop[c];
+            }
+#pragma unroll
+            for(int q = 0; q < 8; q++)
+              if(c0 + q <= cend) slab[(size_t)(c0 + q) * S + rl] = v[q] - l * pt[q];
+          }
           slab[(size_t)kl * S + rl] = l;
         }
       }
       if(rank == 0 && tid == 0) {
         slab[(size_t)kl * S + kl] = d;
-        ipiv[k] = kp + 1;
-        dsub[k] = 0.0;
+        sh.piv[kl] = kp + 1;
+        sh.sub[kl] = 0.0;
       }
     } else {
       // 2x2 pivot on columns k, k+1 (kk = k+1 now holds the candidate column, rows already interchanged)
@@ -373,14 +447,26 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
         sh.dtype[kl] = 2; sh.dtype[kl + 1] = 3;
         sh.d11[kl] = a11; sh.d21[kl] = a21; sh.d22[kl] = a22;
       }
-      for(int rl = tid; rl < S; rl += PT) {
+      for(int rl = tid; rl < S; rl += nthr) {
         const int i = lo + rl;
         if(i < N && i > k + 1) {
           const double w1 = slab[(size_t)kl * S + rl], w2 = slab[(size_t)(kl + 1) * S + rl];
           const double l1 = s2 * (e11 * w1 - w2);
           const double l2 = s2 * (e22 * w2 - w1);
           const int cend = min(nbp - 1, i - k0);
-          for(int c = kl + 2; c <= cend; c++) slab[(size_t)c * S + rl] -= l1 * sh.ptop1[c] + l2 * sh.ptop2[c];
+          for(int c0 = kl + 2; c0 <= cend; c0 += 4) {
+            double v[4], p1[4], p2[4];
+#pragma unroll
+            for(int q = 0; q < 4; q++) {
+              const int c = min(c0 + q, nbp - 1);
+              v[q] = slab[(size_t)c * S + rl];
+              p1[q] = sh.ptop1[c];
+              p2[q] = sh.ptop2[c];
+            }
+#pragma unroll
+            for(int q = 0; q < 4; q++)
+              if(c0 + q <= cend) slab[(size_t)(c0 + q) * S + rl] = v[q] - (l1 * p1[q] + l2 * p2[q]);
+          }
           slab[(size_t)kl * S + rl] = l1;
           slab[(size_t)(kl + 1) * S + rl] = l2;
         }
@@ -389,20 +475,22 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
         slab[(size_t)kl * S + kl] = a11;
         slab[(size_t)kl * S + kl + 1] = 0.0; // L(k+1, k) = 0; d21 lives in dsub
         slab[(size_t)(kl + 1) * S + kl + 1] = a22;
-        ipiv[k] = -(kp + 1);
-        ipiv[k + 1] = -(kp + 1);
-        dsub[k] = a21;
-        dsub[k + 1] = 0.0;
+        sh.piv[kl] = -(kp + 1);
+        sh.piv[kl + 1] = -(kp + 1);
+        sh.sub[kl] = a21;
+        sh.sub[kl + 1] = 0.0;
       }
     }
     k += kstep;
-    __syncthreads();
+    // no CTA barrier here: the next column maximum reads only the thread's own rows, and cta_argmax synchronises before anything
+    // written by other threads (the top of the next column, sh.dtype ...) is read
     PP(5);
   }
+  __syncthreads();
   // ---- write back L for the factored columns, W = L*D for the rows below the panel ----
   const int kb = k - k0;
   const int r0 = k0 + kb;
-  for(int rl = tid; rl < S; rl += PT) {
+  for(int rl = tid; rl < S; rl += nthr) {
     const int i = lo + rl;
     if(i >= N) continue;
     for(int c = 0; c < kb; c++) {
@@ -420,7 +508,8 @@ k_bk_panel(double* __restrict__ A, long long lda, int N, double* __restrict__ W,
     }
   }
   if(rank == 0) {
-    for(int e = tid; e < 2 * nsw; e += PT) swaplog[4 + e] = sh.swaps[e];
+    for(int e = tid; e < kb; e += nthr) { ipiv[k0 + e] = sh.piv[e]; dsub[k0 + e] = sh.sub[e]; }
+    for(int e = tid; e < 2 * nsw; e += nthr) swaplog[4 + e] = sh.swaps[e];
     if(tid == 0) {
       swaplog[0] = nsw; swaplog[1] = k0; swaplog[2] = kb;
       state[1] = kb;
@@ -567,8 +656,10 @@ int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ip
   size_t smem0;
   bkc_geometry(N, &S0, &NB, &smem0);
   if(c->device < 16 && !g_bkc_attr[c->device]) {
-    HB_CUDA(cudaFuncSetAttribute(k_bk_panel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    HB_CUDA(cudaFuncSetAttribute(k_bk_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k_bk_panel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    HB_CUDA(cudaFuncSetAttribute(k_bk_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    HB_CUDA(cudaFuncSetAttribute(k_bk_panel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    HB_CUDA(cudaFuncSetAttribute(k_bk_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     g_bkc_attr[c->device] = true;
   }
   cudaStream_t st = c->stream, side = b->panel_stream;
@@ -584,7 +675,10 @@ int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ip
     if(S < NBMAX) S = NBMAX;
     S = (S + 31) & ~31;
     const size_t smem = ((size_t)NB * S + S) * sizeof(double) + 2 * sizeof(BkStep);
-    k_bk_panel<<<CS, PT, smem, st>>>(A, lda, N, Wp, ldw, NB, S, ipiv_dev, dsub_dev, state_dev, swaplog_dev, p, g_bkc_prof);
+    int threads = S < PT ? S : PT; // one row per thread where possible: fewer idle warps in every barrier / shuffle stage
+    if(threads < 128) threads = 128;
+    if(g_bkc_prof) k_bk_panel<true><<<CS, threads, smem, st>>>(A, lda, N, Wp, ldw, NB, S, ipiv_dev, dsub_dev, state_dev, swaplog_dev, p, g_bkc_prof);
+    else k_bk_panel<false><<<CS, threads, smem, st>>>(A, lda, N, Wp, ldw, NB, S, ipiv_dev, dsub_dev, state_dev, swaplog_dev, p, nullptr);
     HB_LAUNCHED();
     // the interchanges on the previous columns and on the permutation run beside the trailing update (disjoint data)
     HB_CUDA(cudaEventRecord(b->ev_upd, st));

@@ -249,21 +249,18 @@ struct DiagSmem
 // version did them with scalar FMAs on 2 x 2 register tiles and was bound by shared-memory wavefronts: 86 us per block).
 // InvG (global, column-major 128 x 128, zero above the diagonal from allocation): receives the 16 x 16 diagonal inverses here and the
 // off-diagonal blocks in invert_block128.
+// ---- pieces of the 128 x 128 block factorization (16-wide sub-panels) ----
+// warp 0: factor the 16 x 16 diagonal triangle of sub-panel kb in registers (lane = row, shuffles for the pivot row) and invert it
 template <bool LDL>
-__device__ void factor_block128(DiagSmem& S, int k0, int* info, double* __restrict__ InvG, long long* prof)
+__device__ __forceinline__ void subpanel_diag(DiagSmem& S, int kb, int k0, int* info, double* __restrict__ InvG)
 {
-  long long q0 = prof ? clock64() : 0;
-#define QP(slot) if(prof && threadIdx.x == 0) { const long long q1 = clock64(); prof[slot] += q1 - q0; q0 = q1; }
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int gq = lane >> 2, t4 = lane & 3;
-  for(int kb = 0; kb < BB / 16; kb++) {
-    const int c0 = kb * 16;
-    if(warp == 0) {
-      double a[16];
-      double myr = 1.0;
+  const int lane = threadIdx.x & 31;
+  const int c0 = kb * 16;
+  double a[16];
+  double myr = 1.0;
 #pragma unroll
-      for(int c = 0; c < 16; c++) a[c] = (lane < 16 && c <= lane) ? S.D[(c0 + c) * DSB + c0 + lane] : 0.0;
-      // spelled out per column (a rolled 16 x 15 nest would put a[] in local memory)
+  for(int c = 0; c < 16; c++) a[c] = (lane < 16 && c <= lane) ? S.D[(c0 + c) * DSB + c0 + lane] : 0.0;
+  // spelled out per column (a rolled 16 x 15 nest would put a[] in local memory)
 #define BIG_CHOL_COL(j)                                                                          \
   {                                                                                              \
     const double d = __shfl_sync(0xffffffffu, a[j], j);                                          \
@@ -288,106 +285,142 @@ __device__ void factor_block128(DiagSmem& S, int k0, int* info, double* __restri
       if(lane >= c) a[c] -= a[j] * wc;                                                           \
     }                                                                                            \
   }
-      if(LDL) {
-        BIG_LDL_COL(0) BIG_LDL_COL(1) BIG_LDL_COL(2) BIG_LDL_COL(3) BIG_LDL_COL(4) BIG_LDL_COL(5) BIG_LDL_COL(6) BIG_LDL_COL(7)
-        BIG_LDL_COL(8) BIG_LDL_COL(9) BIG_LDL_COL(10) BIG_LDL_COL(11) BIG_LDL_COL(12) BIG_LDL_COL(13) BIG_LDL_COL(14) BIG_LDL_COL(15)
-      } else {
-        BIG_CHOL_COL(0) BIG_CHOL_COL(1) BIG_CHOL_COL(2) BIG_CHOL_COL(3) BIG_CHOL_COL(4) BIG_CHOL_COL(5) BIG_CHOL_COL(6) BIG_CHOL_COL(7)
-        BIG_CHOL_COL(8) BIG_CHOL_COL(9) BIG_CHOL_COL(10) BIG_CHOL_COL(11) BIG_CHOL_COL(12) BIG_CHOL_COL(13) BIG_CHOL_COL(14) BIG_CHOL_COL(15)
-      }
+  if(LDL) {
+    BIG_LDL_COL(0) BIG_LDL_COL(1) BIG_LDL_COL(2) BIG_LDL_COL(3) BIG_LDL_COL(4) BIG_LDL_COL(5) BIG_LDL_COL(6) BIG_LDL_COL(7)
+    BIG_LDL_COL(8) BIG_LDL_COL(9) BIG_LDL_COL(10) BIG_LDL_COL(11) BIG_LDL_COL(12) BIG_LDL_COL(13) BIG_LDL_COL(14) BIG_LDL_COL(15)
+  } else {
+    BIG_CHOL_COL(0) BIG_CHOL_COL(1) BIG_CHOL_COL(2) BIG_CHOL_COL(3) BIG_CHOL_COL(4) BIG_CHOL_COL(5) BIG_CHOL_COL(6) BIG_CHOL_COL(7)
+    BIG_CHOL_COL(8) BIG_CHOL_COL(9) BIG_CHOL_COL(10) BIG_CHOL_COL(11) BIG_CHOL_COL(12) BIG_CHOL_COL(13) BIG_CHOL_COL(14) BIG_CHOL_COL(15)
+  }
 #undef BIG_CHOL_COL
 #undef BIG_LDL_COL
 #pragma unroll
+  for(int c = 0; c < 16; c++)
+    if(lane < 16 && c <= lane) S.D[(c0 + c) * DSB + c0 + lane] = a[c];
+  if(lane < 16) {
+    S.idg[c0 + lane] = myr;
+    if(LDL) {
+      double dl = 0.0;
+#pragma unroll
       for(int c = 0; c < 16; c++)
-        if(lane < 16 && c <= lane) S.D[(c0 + c) * DSB + c0 + lane] = a[c];
-      if(lane < 16) {
-        S.idg[c0 + lane] = myr;
-        if(LDL) {
-          double dl = 0.0;
+        if(c == lane) dl = a[c];
+      S.dv[c0 + lane] = dl;
+      S.rdv[c0 + lane] = 1.0 / dl;
+    }
+  }
+  __syncwarp();
+  // column `lane` of X = T^-1 (T = the 16 x 16 triangle, unit diagonal for LDL^T), right-looking
+  double* inv = S.Inv16 + kb * 16 * 17;
+  double x[16], sacc[16];
 #pragma unroll
-          for(int c = 0; c < 16; c++)
-            if(c == lane) dl = a[c];
-          S.dv[c0 + lane] = dl;
-          S.rdv[c0 + lane] = 1.0 / dl;
-        }
+  for(int r = 0; r < 16; r++) { x[r] = 0.0; sacc[r] = 0.0; }
+#pragma unroll
+  for(int q = 0; q < 16; q++) {
+    const double rq = __shfl_sync(0xffffffffu, myr, q);
+    if(q == lane) x[q] = rq;
+    else if(q > lane) x[q] = -sacc[q] * rq;
+#pragma unroll
+    for(int r = q + 1; r < 16; r++) sacc[r] += S.D[(c0 + q) * DSB + c0 + r] * x[q];
+  }
+  if(lane < 16) {
+#pragma unroll
+    for(int r = 0; r < 16; r++) {
+      inv[r * 17 + lane] = x[r];
+      if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r]; // strictly lower part of the inverse -> the unused upper slots
+      if(InvG && r >= lane) InvG[(size_t)(c0 + lane) * BB + c0 + r] = x[r];
+    }
+  }
+}
+
+// rows below the 16 x 16 triangle: X = A(:, c0:c0+16) T^-T [ D^-1 ] on the DMMA pipe; 8 rows x 16 columns per warp (both column
+// tiles, so the in-place write is safe)
+template <bool LDL>
+__device__ __forceinline__ void subpanel_rows(DiagSmem& S, int kb)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int c0 = kb * 16, below = BB - c0 - 16;
+  const double* inv = S.Inv16 + kb * 16 * 17;
+  for(int rg = warp; rg < below / 8; rg += nwarps) {
+    const int r0 = c0 + 16 + rg * 8;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for(int kk = 0; kk < 4; kk++) {
+      const double af = S.D[(c0 + 4 * kk + t4) * DSB + r0 + gq];
+#pragma unroll
+      for(int nt = 0; nt < 2; nt++) dmma884(acc[nt][0], acc[nt][1], af, inv[(nt * 8 + gq) * 17 + 4 * kk + t4]);
+    }
+    __syncwarp();
+#pragma unroll
+    for(int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) {
+        const int c = nt * 8 + 2 * t4 + h;
+        double v = acc[nt][h];
+        if(LDL) v *= S.rdv[c0 + c];
+        S.D[(c0 + c) * DSB + r0 + gq] = v;
       }
-      __syncwarp();
-      // column `lane` of X = T^-1 (T = the 16 x 16 triangle, unit diagonal for LDL^T), right-looking
-      {
-        double* inv = S.Inv16 + kb * 16 * 17;
-        double x[16], sacc[16];
+  }
+}
+
+// one 8 x 8 tile of the rank-16 update with sub-panel kb: C(i0.., j0..) -= L(i0.., c0:c0+16) [D] L(j0.., c0:c0+16)^T, lower part only
+template <bool LDL>
+__device__ __forceinline__ void rank16_tile(DiagSmem& S, int c0, int i0, int j0)
+{
+  const int lane = threadIdx.x & 31;
+  const int gq = lane >> 2, t4 = lane & 3;
+  double u0 = 0.0, u1 = 0.0;
 #pragma unroll
-        for(int r = 0; r < 16; r++) { x[r] = 0.0; sacc[r] = 0.0; }
-#pragma unroll
-        for(int q = 0; q < 16; q++) {
-          const double rq = __shfl_sync(0xffffffffu, myr, q);
-          if(q == lane) x[q] = rq;
-          else if(q > lane) x[q] = -sacc[q] * rq;
-#pragma unroll
-          for(int r = q + 1; r < 16; r++) sacc[r] += S.D[(c0 + q) * DSB + c0 + r] * x[q];
-        }
-        if(lane < 16) {
-#pragma unroll
-          for(int r = 0; r < 16; r++) {
-            inv[r * 17 + lane] = x[r];
-            if(r > lane) S.D[(c0 + r) * DSB + c0 + lane] = x[r]; // strictly lower part of the inverse -> the unused upper slots
-            if(r >= lane) InvG[(size_t)(c0 + lane) * BB + c0 + r] = x[r];
-          }
-        }
+  for(int kk = 0; kk < 4; kk++) {
+    const double af = S.D[(c0 + 4 * kk + t4) * DSB + i0 + gq];
+    double bf = S.D[(c0 + 4 * kk + t4) * DSB + j0 + gq];
+    if(LDL) bf *= S.dv[c0 + 4 * kk + t4];
+    dmma884(u0, u1, af, bf);
+  }
+  const int i = i0 + gq, j = j0 + 2 * t4;
+  if(i >= j) S.D[j * DSB + i] -= u0;
+  if(i >= j + 1) S.D[(j + 1) * DSB + i] -= u1;
+}
+
+// Factors the 128 x 128 block in S.D. Per 16-wide sub-panel: warp 0 factors and inverts the 16 x 16 diagonal triangle (the serial
+// part, ~5000 cycles); the rows below and the rank-16 update run on the DMMA pipe straight out of shared memory (the first version did
+// them with scalar FMAs on 2 x 2 register tiles and was bound by shared-memory wavefronts: 86 us per block). The update is split:
+// the 16 columns of the NEXT sub-panel first (all warps), then warp 0 already factors the next triangle while the other warps
+// finish the rest of the update.
+template <bool LDL>
+__device__ void factor_block128(DiagSmem& S, int k0, int* info, double* __restrict__ InvG, long long* prof)
+{
+  const int warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  long long q0 = prof ? clock64() : 0;
+#define QP(slot) if(prof && threadIdx.x == 0) { const long long q1 = clock64(); prof[slot] += q1 - q0; q0 = q1; }
+  if(warp == 0) subpanel_diag<LDL>(S, 0, k0, info, InvG);
+  __syncthreads();
+  QP(1);
+  for(int kb = 0; kb < BB / 16; kb++) {
+    const int c0 = kb * 16, below = BB - c0 - 16, nt8 = below / 8;
+    subpanel_rows<LDL>(S, kb);
+    __syncthreads();
+    QP(2);
+    if(nt8 == 0) break;
+    // strip: the two 8-column tile columns of the next sub-panel
+    for(int t = warp; t < 2 * nt8 - 1; t += nwarps) {
+      const int tjc = t < nt8 ? 0 : 1, ti = t < nt8 ? t : t - nt8 + 1;
+      rank16_tile<LDL>(S, c0, c0 + 16 + 8 * ti, c0 + 16 + 8 * tjc);
+    }
+    __syncthreads();
+    QP(3);
+    if(warp == 0) {
+      subpanel_diag<LDL>(S, kb + 1, k0, info, InvG);
+    } else {
+      const int m = nt8 - 2; // tile columns 2.. : lower triangle of order m
+      for(int t = warp - 1; t < m * (m + 1) / 2; t += nwarps - 1) {
+        int ti = 0, rem = t;
+        while(rem > ti) { rem -= ti + 1; ti++; }
+        rank16_tile<LDL>(S, c0, c0 + 16 + 8 * (ti + 2), c0 + 16 + 8 * (rem + 2));
       }
     }
     __syncthreads();
     QP(1);
-    const int below = BB - c0 - 16;
-    {
-      // rows below: X = A(:, c0:c0+16) T^-T [ D^-1 ], 8 rows x 16 columns per warp (both column tiles, so the in-place write is safe)
-      const double* inv = S.Inv16 + kb * 16 * 17;
-      for(int rg = warp; rg < below / 8; rg += DTHREADS / 32) {
-        const int r0 = c0 + 16 + rg * 8;
-        double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
-#pragma unroll
-        for(int kk = 0; kk < 4; kk++) {
-          const double af = S.D[(c0 + 4 * kk + t4) * DSB + r0 + gq];
-#pragma unroll
-          for(int nt = 0; nt < 2; nt++) dmma884(acc[nt][0], acc[nt][1], af, inv[(nt * 8 + gq) * 17 + 4 * kk + t4]);
-        }
-        __syncwarp();
-#pragma unroll
-        for(int nt = 0; nt < 2; nt++)
-#pragma unroll
-          for(int h = 0; h < 2; h++) {
-            const int c = nt * 8 + 2 * t4 + h;
-            double v = acc[nt][h];
-            if(LDL) v *= S.rdv[c0 + c];
-            S.D[(c0 + c) * DSB + r0 + gq] = v;
-          }
-      }
-    }
-    __syncthreads();
-    QP(2);
-    {
-      // rank-16 update of the remaining lower triangle, 8 x 8 tiles dealt to the warps
-      const int nt8 = below / 8;
-      const int ntiles = nt8 * (nt8 + 1) / 2;
-      for(int t = warp; t < ntiles; t += DTHREADS / 32) {
-        int ti = 0, rem = t;
-        while(rem > ti) { rem -= ti + 1; ti++; }
-        const int i0 = c0 + 16 + 8 * ti, j0 = c0 + 16 + 8 * rem;
-        double u0 = 0.0, u1 = 0.0;
-#pragma unroll
-        for(int kk = 0; kk < 4; kk++) {
-          const double af = S.D[(c0 + 4 * kk + t4) * DSB + i0 + gq];
-          double bf = S.D[(c0 + 4 * kk + t4) * DSB + j0 + gq];
-          if(LDL) bf *= S.dv[c0 + 4 * kk + t4];
-          dmma884(u0, u1, af, bf);
-        }
-        const int i = i0 + gq, j = j0 + 2 * t4;
-        if(i >= j) S.D[j * DSB + i] -= u0;
-        if(i >= j + 1) S.D[(j + 1) * DSB + i] -= u1;
-      }
-    }
-    __syncthreads();
-    QP(3);
   }
 #undef QP
 }
@@ -431,7 +464,7 @@ __device__ void invert_block128(DiagSmem& S, double* __restrict__ InvG)
 
 template <bool LDL>
 __global__ void __launch_bounds__(DTHREADS, 1)
-k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restrict__ InvG, double* __restrict__ dinvG, int* __restrict__ info,
+k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restrict__ inv16G, double* __restrict__ dinvG, int* __restrict__ info,
           long long* __restrict__ prof /* NULL, or 8 cycle counters of thread 0: load, 16x16 factor+inverse, rows below, rank-16 update, store, inversion */)
 {
   long long t0 = prof ? clock64() : 0;
@@ -440,25 +473,122 @@ k_diag128(double* __restrict__ A, long long lda, int N, int k0, double* __restri
   DiagSmem& S = *reinterpret_cast<DiagSmem*>(dsm_raw);
   const int tid = threadIdx.x;
   const int nb = min(BB, N - k0);
-  for(int e = tid; e < BB * BB; e += DTHREADS) {
-    const int j = e / BB, i = e % BB;
-    double v = (i == j) ? 1.0 : 0.0;
-    if(i < nb && j < nb && i >= j) v = LC(A, lda, k0 + i, k0 + j);
-    S.D[j * DSB + i] = v;
+  for(int e0 = tid; e0 < BB * BB; e0 += DTHREADS * 8) { // 8 independent loads in flight per thread
+    double v[8];
+#pragma unroll
+    for(int q = 0; q < 8; q++) {
+      const int e = e0 + q * DTHREADS;
+      const int j = e / BB, i = e % BB;
+      v[q] = (i == j) ? 1.0 : 0.0;
+      if(i < nb && j < nb && i >= j) v[q] = LC(A, lda, k0 + i, k0 + j);
+    }
+#pragma unroll
+    for(int q = 0; q < 8; q++) {
+      const int e = e0 + q * DTHREADS;
+      S.D[(e / BB) * DSB + e % BB] = v[q];
+    }
   }
   __syncthreads();
   DP(0);
-  factor_block128<LDL>(S, k0, info, InvG, prof);
+  factor_block128<LDL>(S, k0, info, nullptr, prof);
   if(prof) t0 = clock64();
   for(int e = tid; e < nb * nb; e += DTHREADS) {
     const int j = e / nb, i = e % nb;
     if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DSB + i];
   }
   if(LDL && tid < BB) dinvG[tid] = S.rdv[tid];
+  for(int e = tid; e < 8 * 16 * 17; e += DTHREADS) inv16G[e] = S.Inv16[e]; // the panel solve below the block uses the 16 x 16 inverses
   DP(4);
-  invert_block128(S, InvG);
-  DP(5);
 #undef DP
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Panel solve below a factored diagonal block: X = A21 L11^-T by BLOCK SUBSTITUTION with the 16 x 16 diagonal inverses
+// (half the flops of a product with the explicit 128 x 128 inverse, and that inverse leaves the critical path: it is only needed by
+// the solves and is built for all blocks at once after the factorization). One CTA per 64 rows; warp w owns rows 8w..8w+7 for all
+// eight column blocks, so the whole recurrence needs no CTA-wide barrier. LDL^T: X = W = L21 D; L21 = W D^-1 is formed on the way out.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int XROWS = 64;
+constexpr int XS = XROWS + 4;
+struct TrsmSmem
+{
+  double L[BB * DSB];     // L[q*DSB + r] = L11(r, q)
+  double Inv16[8 * 16 * 17];
+  double X[BB * XS];      // X[c*XS + r] = element (row r of the tile, column c)
+};
+
+template <bool LDL>
+__global__ void __launch_bounds__(256, 1)
+k_trsm_panel(double* __restrict__ A, long long lda, int N, int k0, const double* __restrict__ inv16G, const double* __restrict__ dinvG,
+             double* __restrict__ W2, long long ldw2)
+{
+  extern __shared__ __align__(16) unsigned char tsm_raw[];
+  TrsmSmem& S = *reinterpret_cast<TrsmSmem*>(tsm_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t4 = lane & 3;
+  const int r0g = k0 + BB;                    // first row below the block
+  const int i0 = r0g + XROWS * blockIdx.x;    // first row of this tile
+  // ---- loads (16-byte cp.async, all in flight at once): L11, the 16 x 16 inverses, the A21 tile. The upper part of L11 is copied as
+  //      it lies in memory (never read: the recurrence only touches entries strictly below the 16 x 16 diagonal blocks). ----
+  for(int e = tid; e < BB * BB / 2; e += 256) {
+    const int j = e / (BB / 2), i = (e % (BB / 2)) * 2;
+    cp_async16(&S.L[j * DSB + i], &LC(A, lda, k0 + i, k0 + j), 16);
+  }
+  for(int e = tid; e < BB * XROWS / 2; e += 256) {
+    const int c = e / (XROWS / 2), r = (e % (XROWS / 2)) * 2;
+    const bool v = i0 + r < N;
+    cp_async16(&S.X[c * XS + r], v ? &LC(A, lda, i0 + r, k0 + c) : A, v ? 16 : 0);
+  }
+  for(int e = tid; e < 8 * 16 * 17; e += 256) S.Inv16[e] = inv16G[e];
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int rw = warp * 8; // my 8 rows
+  for(int jb = 0; jb < BB / 16; jb++) {
+    const int cb = 16 * jb;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    for(int q0 = 0; q0 < cb; q0 += 4) {
+      const double af = S.X[(q0 + t4) * XS + rw + gq];
+#pragma unroll
+      for(int nt = 0; nt < 2; nt++) dmma884(acc[nt][0], acc[nt][1], af, S.L[(q0 + t4) * DSB + cb + 8 * nt + gq]);
+    }
+    // Y = A - sum (my C-fragment elements), in place
+#pragma unroll
+    for(int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) {
+        double* px = &S.X[(cb + 8 * nt + 2 * t4 + h) * XS + rw + gq];
+        *px = *px - acc[nt][h];
+      }
+    __syncwarp();
+    const double* inv = S.Inv16 + jb * 16 * 17;
+    double ac2[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+    for(int kk = 0; kk < 4; kk++) {
+      const double af = S.X[(cb + 4 * kk + t4) * XS + rw + gq];
+#pragma unroll
+      for(int nt = 0; nt < 2; nt++) dmma884(ac2[nt][0], ac2[nt][1], af, inv[(nt * 8 + gq) * 17 + 4 * kk + t4]);
+    }
+    __syncwarp();
+#pragma unroll
+    for(int nt = 0; nt < 2; nt++)
+#pragma unroll
+      for(int h = 0; h < 2; h++) S.X[(cb + 8 * nt + 2 * t4 + h) * XS + rw + gq] = ac2[nt][h];
+    __syncwarp();
+  }
+  __syncthreads();
+  for(int e = tid; e < BB * XROWS; e += 256) {
+    const int c = e / XROWS, r = e % XROWS;
+    const int i = i0 + r;
+    if(i >= N) continue;
+    const double x = S.X[c * XS + r];
+    if(LDL) {
+      W2[(size_t)c * ldw2 + i] = x;
+      LC(A, lda, i, k0 + c) = x * dinvG[c];
+    } else {
+      LC(A, lda, i, k0 + c) = x;
+    }
+  }
 }
 
 // Inverses of the 128 x 128 diagonal triangles of an EXISTING factor (paths that do not run k_diag128: cooperative Cholesky,
@@ -715,6 +845,8 @@ int ensure_attrs(hb_ctx* c)
   HB_CUDA(cudaFuncSetAttribute(k_diag128<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
   HB_CUDA(cudaFuncSetAttribute(k_diag128<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
   HB_CUDA(cudaFuncSetAttribute(k_block_inverses, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DiagSmem)));
+  HB_CUDA(cudaFuncSetAttribute(k_trsm_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsmSmem)));
+  HB_CUDA(cudaFuncSetAttribute(k_trsm_panel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TrsmSmem)));
   if(c->device < 16) g_big_attr[c->device] = true;
   return HB_OK;
 }
@@ -766,7 +898,7 @@ int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w)
       return hb_fail(HB_ERR_ALLOC, "hb_big_reserve: scratch allocation failed%s", "");
     }
     HB_CUDA(cudaMemsetAsync(b->InvAll, 0, sizeof(double) * (size_t)nblk * BB * BB, c->stream)); // the kernels only write the lower triangles
-    if(!b->dinv) HB_CUDA(cudaMalloc(&b->dinv, sizeof(double) * BB));
+    if(!b->dinv) HB_CUDA(cudaMalloc(&b->dinv, sizeof(double) * (BB + 8 * 16 * 17)));
     if(!b->counter) {
       HB_CUDA(cudaMalloc(&b->counter, sizeof(int) * 4));
       HB_CUDA(cudaMemsetAsync(b->counter, 0, sizeof(int) * 4, c->stream));
@@ -796,24 +928,17 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
   const int nblk = (N + BB - 1) / BB;
   for(int blk = 0; blk < nblk; blk++) {
     const int k0 = blk * BB, nb = N - k0 < BB ? N - k0 : BB, r0 = k0 + nb;
-    double* InvG = b->InvAll + (size_t)blk * BB * BB;
+    double* inv16 = b->dinv + BB;
     double* Wb = ldl ? b->W[blk & 1] : nullptr;
     // ---- panel stream: diagonal block, then L21 ----
     HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd, 0));
-    if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev, nullptr);
-    else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, InvG, b->dinv, info_dev, nullptr);
+    if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, info_dev, nullptr);
+    else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, info_dev, nullptr);
     HB_LAUNCHED();
-    if(r0 < N) {
-      GemmArgs g{};
-      g.P = A + (size_t)k0 * lda; g.ldp = lda;
-      g.Q = InvG; g.ldq = BB; g.qsub = k0;
-      g.kb = nb;
-      g.C = A; g.ldc = lda;
-      g.i_base = r0; g.j_base = k0; g.i_end = N; g.j_end = r0; g.tj0 = 0;
-      g.W2 = Wb; g.ldw2 = ldw; g.dinv = b->dinv; g.state = nullptr;
-      const dim3 grid((N - r0 + TM - 1) / TM, 1);
-      if(ldl) k_gemm_pq<128, EPI_STORE_LDL><<<grid, 256, GemmCfg<128>::SMEM, sp>>>(g);
-      else k_gemm_pq<128, EPI_STORE><<<grid, 256, GemmCfg<128>::SMEM, sp>>>(g);
+    if(r0 < N) { // nb == 128 here (only the last block can be partial)
+      const int ntile = (N - r0 + XROWS - 1) / XROWS;
+      if(ldl) k_trsm_panel<true><<<ntile, 256, sizeof(TrsmSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, Wb, ldw);
+      else k_trsm_panel<false><<<ntile, 256, sizeof(TrsmSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, nullptr, 0);
       HB_LAUNCHED();
     }
     HB_CUDA(cudaEventRecord(b->ev_panel, sp));
@@ -839,6 +964,9 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
       }
     }
   }
+  // the 128 x 128 inverses of the diagonal triangles (for the solves), all blocks at once
+  k_block_inverses<<<nblk, DTHREADS, sizeof(DiagSmem), su>>>(A, lda, N, ldl ? 1 : 0, b->InvAll);
+  HB_LAUNCHED();
   b->inv_valid = true;
   return HB_OK;
 }
@@ -853,8 +981,8 @@ int hb_big_diag_profile(hb_ctx* c, hb_big* b, int N, double* A, long long lda, i
   int* info = nullptr;
   HB_CUDA(cudaMalloc(&info, sizeof(int)));
   HB_CUDA(cudaMemsetAsync(info, 0, sizeof(int), c->stream));
-  if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->InvAll, b->dinv, info, prof);
-  else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->InvAll, b->dinv, info, prof);
+  if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->dinv + BB, b->dinv, info, prof);
+  else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), c->stream>>>(A, lda, N, k0, b->dinv + BB, b->dinv, info, prof);
   HB_LAUNCHED();
   HB_CUDA(cudaMemcpyAsync(prof_host8, prof, sizeof(long long) * 8, cudaMemcpyDeviceToHost, c->stream));
   HB_CUDA(cudaStreamSynchronize(c->stream));

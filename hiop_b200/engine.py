@@ -62,6 +62,12 @@ class Context:
     def sync(self):
         check(self.L.hb_ctx_sync(self.h), "hb_ctx_sync")
 
+    def microbench_peak(self, which: int) -> float:
+        """0: FP64 DMMA TFLOP/s, 1: int8 tcgen05 TOP/s -- measured on this device, now (hb_microbench_peak)"""
+        v = ctypes.c_double()
+        check(self.L.hb_microbench_peak(self.h, which, ctypes.byref(v)), "hb_microbench_peak")
+        return v.value
+
     def close(self):
         if self.h:
             self.L.hb_ctx_destroy(self.h)

@@ -60,6 +60,11 @@ int hb_ctx_device(hb_ctx* ctx);
 int hb_ctx_enable_timing(hb_ctx* ctx, int on);
 int hb_ctx_last_syrk_ms(hb_ctx* ctx, float* ms_host);
 
+/* Measured roofline denominators of this device (a few milliseconds each, CUDA events on the context stream):
+ * which = 0: FP64 tensor pipe, mma.sync.m8n8k4.f64 issued back to back from registers (TFLOP/s);
+ * which = 1: tcgen05.mma.kind::i8 M=128 N=256 K=32 issued back to back on resident operands (TOP/s, 2 ops per MAC). */
+int hb_microbench_peak(hb_ctx* ctx, int which, double* result_host);
+
 int hb_malloc(hb_ctx* ctx, size_t bytes, void** dptr);
 int hb_free(hb_ctx* ctx, void* dptr);
 int hb_malloc_host(hb_ctx* ctx, size_t bytes, void** hptr); /* pinned */
@@ -149,6 +154,10 @@ int hb_symdense_solve(hb_symdense* s, double* x, int nrhs);
 /* host-buffer convenience used by the C++ adapter when mem_space is host: uploads the upper triangle, factorizes */
 int hb_symdense_matrix_changed_host(hb_symdense* s, const double* M_host, int mode);
 int hb_symdense_solve_host(hb_symdense* s, double* x_host, int nrhs);
+/* diagnostics (tools/prof_diag.py): cycle counters of the phases of the two kernels on the critical path of the large-N factorizations
+ * (the 128 x 128 diagonal-block kernel on the leading block of M; the cluster Bunch-Kaufman panel, summed over a factorization) */
+int hb_debug_diag128_profile(hb_symdense* s, int ldl, long long* prof_host8);
+int hb_debug_bk_profile(hb_ctx* ctx, int on, long long* prof_host8);
 
 /* ------------------------------------------------------------------------------------------------------------
  * hiopKKTLinSysLowRank + hiopHessianLowRank (B2; src/Optimization/hiopKKTLinSys.cpp:1031-1350,
