@@ -120,6 +120,9 @@ def lib() -> ctypes.CDLL:
     f("hb_lowrank_set_secant", c_i, c_vp, c_i, c_d, c_dp, c_dp, c_vp, c_vp)
     f("hb_lowrank_update", c_i, c_vp, *([c_dp] * 8))
     f("hb_lowrank_condense", c_i, c_vp)
+    f("hb_lowrank_condense_async", c_i, c_vp)
+    f("hb_lowrank_check", c_i, c_vp)
+    f("hb_lowrank_fallback_count", c_i, c_vp)
     f("hb_lowrank_set_condense_mode", c_i, c_vp, c_i)
     f("hb_lowrank_get_condense_mode", c_i, c_vp)
     f("hb_lowrank_solve_compressed", c_i, c_vp, *([c_dp] * 6))

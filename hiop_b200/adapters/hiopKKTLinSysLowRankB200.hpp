@@ -38,5 +38,11 @@ private:
   double *dpat_[4], *dit_[8], *drhs_[3], *dsol_[3];
   double *dres_[12], *ddir_[12]; // allocated on the first device-side refinement
   bool ir_on_device_;
+  bool healthy_;   // false after an engine error: every entry point then answers false (the reference's failure value), nothing aborts
+  // Jacobian traffic and timing (HIOP_B200_STATS=1 prints them when the object dies)
+  int n_updates_ = 0, n_jac_uploads_ = 0, n_dirs_ = 0;
+  long long jac_evals_seen_ = -1;
+  unsigned long long jac_hash_ = 0;
+  double jac_bytes_first_ = 0.0, jac_bytes_later_ = 0.0, t_update_ = 0.0, t_dirs_ = 0.0;
 };
 } // namespace hiop

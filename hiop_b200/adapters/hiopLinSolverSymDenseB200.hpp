@@ -12,8 +12,9 @@ namespace hiop
 class hiopLinSolverSymDenseB200 : public hiopLinSolverSymDense
 {
 public:
-  /// mode: HB_FACT_BUNCH_KAUFMAN (safe mode, MagmaBuKa role) or HB_FACT_NOPIV (speculative mode, MagmaNopiv role)
-  hiopLinSolverSymDenseB200(int n, hiopNlpFormulation* nlp, int mode);
+  /// safe_mode: pointer to the owning KKT object's safe-mode flag, read at every matrixChanged(): Bunch-Kaufman while it is set
+  /// (MagmaBuKa role), LDL^T without pivoting otherwise (MagmaNopiv role). NULL = always Bunch-Kaufman.
+  hiopLinSolverSymDenseB200(int n, hiopNlpFormulation* nlp, const bool* safe_mode);
   virtual ~hiopLinSolverSymDenseB200();
   int matrixChanged() override;
   bool solve(hiopVector& x) override;
@@ -21,6 +22,7 @@ public:
 private:
   hb_ctx* ctx_;
   hb_symdense* h_;
-  int mode_;
+  const bool* safe_mode_;
+  bool healthy_;
 };
 } // namespace hiop

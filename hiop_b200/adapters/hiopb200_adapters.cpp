@@ -11,29 +11,44 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 
 namespace hiop
 {
 namespace
 {
+// One engine context per process. A failure (no sm_100 device, ...) is NOT fatal here: the adapters remember it and answer with the
+// reference's own failure values -- update() / solve() false, matrixChanged() -1 -- so that the driver escalates exactly as it does for a
+// failed factorization (hiopAlgFilterIPM.cpp:1216-1229); nothing in this file calls exit().
 hb_ctx* shared_ctx()
 {
   static hb_ctx* ctx = nullptr;
-  if(!ctx) {
+  static bool tried = false;
+  if(!tried) {
+    tried = true;
     const char* dev = getenv("HIOP_B200_DEVICE");
     if(hb_ctx_create(dev ? atoi(dev) : 0, &ctx) != HB_OK) {
       fprintf(stderr, "hiop-b200: %s\n", hb_last_error());
-      exit(EXIT_FAILURE); // like the reference's hard failures on missing back-ends (hiopNlpFormulation.cpp:360-363)
+      ctx = nullptr;
     }
   }
   return ctx;
 }
-void must(int rc, const char* what)
+// records the first engine error of an adapter object; returns true when rc is HB_OK
+bool ok(int rc, const char* what, bool* healthy)
 {
-  if(rc != HB_OK) {
-    fprintf(stderr, "hiop-b200: %s failed: %s\n", what, hb_last_error());
-    exit(EXIT_FAILURE);
-  }
+  if(rc == HB_OK) return true;
+  fprintf(stderr, "hiop-b200: %s failed: %s\n", what, hb_last_error());
+  if(healthy) *healthy = false;
+  return false;
+}
+// 64-bit FNV-1a over the raw bytes: constant-Jacobian detection for problems that do not declare themselves linear (small J only)
+unsigned long long fnv1a(const void* p, size_t bytes)
+{
+  const unsigned long long* w = static_cast<const unsigned long long*>(p);
+  unsigned long long h = 1469598103934665603ull;
+  for(size_t i = 0; i < bytes / 8; i++) { h ^= w[i]; h *= 1099511628211ull; }
+  return h;
 }
 } // namespace
 
@@ -49,32 +64,36 @@ hiopKKTLinSysLowRank* hiop_b200_new_lowrank_kkt(hiopNlpFormulation* nlp)
   return new hiopKKTLinSysLowRank(nlp);
 }
 
-hiopLinSolverSymDense* hiop_b200_new_symdense_solver(int n, hiopNlpFormulation* nlp, bool safe_mode)
+hiopLinSolverSymDense* hiop_b200_new_symdense_solver(int n, hiopNlpFormulation* nlp, const bool* safe_mode)
 {
-  if(hiop_b200_enabled()) {
-    const char* force = getenv("HIOP_B200_LINSOL"); // "bk" | "nopiv": overrides the safe_mode choice
-    int mode = safe_mode ? HB_FACT_BUNCH_KAUFMAN : HB_FACT_NOPIV;
-    if(force && !strcmp(force, "bk")) mode = HB_FACT_BUNCH_KAUFMAN;
-    if(force && !strcmp(force, "nopiv")) mode = HB_FACT_NOPIV;
-    return new hiopLinSolverSymDenseB200(n, nlp, mode);
-  }
+  if(hiop_b200_enabled()) return new hiopLinSolverSymDenseB200(n, nlp, safe_mode);
   return new hiopLinSolverSymDenseLapack(n, nlp);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-hiopLinSolverSymDenseB200::hiopLinSolverSymDenseB200(int n, hiopNlpFormulation* nlp, int mode)
-  : hiopLinSolverSymDense(n, nlp), ctx_(shared_ctx()), h_(nullptr), mode_(mode)
+hiopLinSolverSymDenseB200::hiopLinSolverSymDenseB200(int n, hiopNlpFormulation* nlp, const bool* safe_mode)
+  : hiopLinSolverSymDense(n, nlp), ctx_(shared_ctx()), h_(nullptr), safe_mode_(safe_mode), healthy_(true)
 {
-  must(hb_symdense_create(ctx_, n, &h_), "hb_symdense_create");
+  if(!ctx_) { healthy_ = false; return; }
+  ok(hb_symdense_create(ctx_, n, &h_), "hb_symdense_create", &healthy_);
 }
-hiopLinSolverSymDenseB200::~hiopLinSolverSymDenseB200() { hb_symdense_destroy(h_); }
+hiopLinSolverSymDenseB200::~hiopLinSolverSymDenseB200() { if(h_) hb_symdense_destroy(h_); }
 
 int hiopLinSolverSymDenseB200::matrixChanged()
 {
+  if(!healthy_) return -1;
+  // The factorization follows the KKT object's CURRENT safe mode (read through the pointer on every call): Bunch-Kaufman when
+  // safe_mode is on (MagmaBuKa role), LDL^T without pivoting otherwise (MagmaNopiv role). The non-MAGMA build of the reference
+  // never re-creates linSys_ when safe_mode flips (hiopKKTLinSysMDS.cpp:405-430 does so only under HIOP_USE_MAGMA), so a mode
+  // frozen at construction would lose the reference's stability fallback.
+  int mode = (safe_mode_ == nullptr || *safe_mode_) ? HB_FACT_BUNCH_KAUFMAN : HB_FACT_NOPIV;
+  const char* force = getenv("HIOP_B200_LINSOL"); // "bk" | "nopiv": overrides the safe_mode choice
+  if(force && !strcmp(force, "bk")) mode = HB_FACT_BUNCH_KAUFMAN;
+  if(force && !strcmp(force, "nopiv")) mode = HB_FACT_NOPIV;
   nlp_->runStats.linsolv.tmFactTime.start();
   // M_ lives in host memory (mem_space=default): upload + factorize (the MAGMA twin does the same H2D per factorization,
   // hiopLinSolverSymDenseMagma.cpp:139-146)
-  const int ret = hb_symdense_matrix_changed_host(h_, M_->local_data(), mode_);
+  const int ret = hb_symdense_matrix_changed_host(h_, M_->local_data(), mode);
   nlp_->runStats.linsolv.tmFactTime.stop();
   if(ret < -1) {
     nlp_->log->printf(hovError, "hiopLinSolverSymDenseB200: %s\n", hb_last_error());
@@ -85,6 +104,7 @@ int hiopLinSolverSymDenseB200::matrixChanged()
 
 bool hiopLinSolverSymDenseB200::solve(hiopVector& x)
 {
+  if(!healthy_) return false;
   nlp_->runStats.linsolv.tmTriuSolves.start();
   const int rc = hb_symdense_solve_host(h_, x.local_data(), 1);
   nlp_->runStats.linsolv.tmTriuSolves.stop();
@@ -93,40 +113,64 @@ bool hiopLinSolverSymDenseB200::solve(hiopVector& x)
 
 // ---------------------------------------------------------------------------------------------------------
 hiopKKTLinSysLowRankB200::hiopKKTLinSysLowRankB200(hiopNlpFormulation* nlp)
-  : hiopKKTLinSysLowRank(nlp), ctx_(shared_ctx()), h_(nullptr), dJ_(nullptr), dSt_(nullptr), dYt_(nullptr)
+  : hiopKKTLinSysLowRank(nlp), ctx_(shared_ctx()), h_(nullptr), dJ_(nullptr), dSt_(nullptr), dYt_(nullptr), healthy_(true)
 {
   for(int i = 0; i < 12; i++) dres_[i] = ddir_[i] = nullptr;
+  for(auto*& p : dpat_) p = nullptr;
+  for(auto*& p : dit_) p = nullptr;
+  for(auto*& p : drhs_) p = nullptr;
+  for(auto*& p : dsol_) p = nullptr;
   const char* ir = getenv("HIOP_B200_IR");
   ir_on_device_ = !(ir && !strcmp(ir, "host"));
   n_ = nlp_->n_local();
   meq_ = nlp_->m_eq();
   mineq_ = nlp_->m_ineq();
   lmax_ = nlp_->options->GetInteger("secant_memory_len");
-  must(hb_lowrank_create(ctx_, n_, meq_, mineq_, lmax_ > 0 ? lmax_ : 1, &h_), "hb_lowrank_create");
-  const size_t m = (size_t)meq_ + mineq_;
-  must(hb_malloc(ctx_, sizeof(double) * m * n_, (void**)&dJ_), "hb_malloc(J)");
-  must(hb_malloc(ctx_, sizeof(double) * (size_t)(lmax_ > 0 ? lmax_ : 1) * n_, (void**)&dSt_), "hb_malloc(S)");
-  must(hb_malloc(ctx_, sizeof(double) * (size_t)(lmax_ > 0 ? lmax_ : 1) * n_, (void**)&dYt_), "hb_malloc(Y)");
-  const size_t psz[4] = {(size_t)n_, (size_t)n_, (size_t)mineq_, (size_t)mineq_};
-  for(int i = 0; i < 4; i++) must(hb_malloc(ctx_, sizeof(double) * psz[i], (void**)&dpat_[i]), "hb_malloc(pattern)");
-  const size_t isz[8] = {(size_t)n_, (size_t)n_, (size_t)n_, (size_t)n_, (size_t)mineq_, (size_t)mineq_, (size_t)mineq_, (size_t)mineq_};
-  for(int i = 0; i < 8; i++) must(hb_malloc(ctx_, sizeof(double) * isz[i], (void**)&dit_[i]), "hb_malloc(iterate)");
-  const size_t rsz[3] = {(size_t)n_, (size_t)meq_, (size_t)mineq_};
-  for(int i = 0; i < 3; i++) {
-    must(hb_malloc(ctx_, sizeof(double) * rsz[i], (void**)&drhs_[i]), "hb_malloc(rhs)");
-    must(hb_malloc(ctx_, sizeof(double) * rsz[i], (void**)&dsol_[i]), "hb_malloc(sol)");
+  if(!ctx_) { healthy_ = false; return; }
+#ifdef HIOP_USE_MPI
+  if(nlp_->get_num_ranks() > 1) {
+    // the engine context of this adapter is single-GPU: with an MPI-distributed HiOp the condensed matrix, the multi-dots and J dx
+    // would be reduced over the local columns only. (The C-ABI itself shards over NCCL, hb_comm_init; bootstrapping its id over MPI is
+    // the missing piece.) Refuse instead of computing wrong directions.
+    fprintf(stderr, "hiop-b200: hiopKKTLinSysLowRankB200 does not support MPI-distributed problems (%d ranks); use the reference classes\n",
+            nlp_->get_num_ranks());
+    healthy_ = false;
+    return;
   }
+#endif
+  if(!ok(hb_lowrank_create(ctx_, n_, meq_, mineq_, lmax_ > 0 ? lmax_ : 1, &h_), "hb_lowrank_create", &healthy_)) return;
+  const size_t m = (size_t)meq_ + mineq_;
+  bool a = ok(hb_malloc(ctx_, sizeof(double) * m * n_, (void**)&dJ_), "hb_malloc(J)", &healthy_);
+  a = a && ok(hb_malloc(ctx_, sizeof(double) * (size_t)(lmax_ > 0 ? lmax_ : 1) * n_, (void**)&dSt_), "hb_malloc(S)", &healthy_);
+  a = a && ok(hb_malloc(ctx_, sizeof(double) * (size_t)(lmax_ > 0 ? lmax_ : 1) * n_, (void**)&dYt_), "hb_malloc(Y)", &healthy_);
+  const size_t psz[4] = {(size_t)n_, (size_t)n_, (size_t)mineq_, (size_t)mineq_};
+  for(int i = 0; i < 4 && a; i++) a = ok(hb_malloc(ctx_, sizeof(double) * psz[i], (void**)&dpat_[i]), "hb_malloc(pattern)", &healthy_);
+  const size_t isz[8] = {(size_t)n_, (size_t)n_, (size_t)n_, (size_t)n_, (size_t)mineq_, (size_t)mineq_, (size_t)mineq_, (size_t)mineq_};
+  for(int i = 0; i < 8 && a; i++) a = ok(hb_malloc(ctx_, sizeof(double) * isz[i], (void**)&dit_[i]), "hb_malloc(iterate)", &healthy_);
+  const size_t rsz[3] = {(size_t)n_, (size_t)meq_, (size_t)mineq_};
+  for(int i = 0; i < 3 && a; i++) {
+    a = ok(hb_malloc(ctx_, sizeof(double) * rsz[i], (void**)&drhs_[i]), "hb_malloc(rhs)", &healthy_);
+    a = a && ok(hb_malloc(ctx_, sizeof(double) * rsz[i], (void**)&dsol_[i]), "hb_malloc(sol)", &healthy_);
+  }
+  if(!a) return;
   // patterns are fixed for the lifetime of the formulation
   upload(dpat_[0], nlp_->get_ixl().local_data_const(), n_);
   upload(dpat_[1], nlp_->get_ixu().local_data_const(), n_);
   upload(dpat_[2], nlp_->get_idl().local_data_const(), mineq_);
   upload(dpat_[3], nlp_->get_idu().local_data_const(), mineq_);
-  must(hb_lowrank_set_patterns(h_, dpat_[0], dpat_[1], dpat_[2], dpat_[3]), "hb_lowrank_set_patterns");
+  ok(hb_lowrank_set_patterns(h_, dpat_[0], dpat_[1], dpat_[2], dpat_[3]), "hb_lowrank_set_patterns", &healthy_);
 }
 
 hiopKKTLinSysLowRankB200::~hiopKKTLinSysLowRankB200()
 {
-  hb_lowrank_destroy(h_);
+  if(getenv("HIOP_B200_STATS") && n_updates_ > 0) {
+    // per-iteration KKT time of the engine path, next to the reference's own tmSolverInternal / time_kkt output
+    fprintf(stderr, "hiop-b200 stats: updates %d, Jacobian uploads %d (first %.0f bytes, after the first %.0f bytes), KKT update+condense %.3f ms/it, "
+            "directions %.3f ms/call (%d calls)\n", n_updates_, n_jac_uploads_, jac_bytes_first_, jac_bytes_later_, 1e3 * t_update_ / n_updates_,
+            n_dirs_ ? 1e3 * t_dirs_ / n_dirs_ : 0.0, n_dirs_);
+  }
+  if(h_) hb_lowrank_destroy(h_);
+  if(!ctx_) return;
   hb_free(ctx_, dJ_); hb_free(ctx_, dSt_); hb_free(ctx_, dYt_);
   for(auto* p : dpat_) hb_free(ctx_, p);
   for(auto* p : dit_) hb_free(ctx_, p);
@@ -139,36 +183,62 @@ hiopKKTLinSysLowRankB200::~hiopKKTLinSysLowRankB200()
 bool hiopKKTLinSysLowRankB200::upload(double* dst, const double* src, size_t count)
 {
   if(count == 0) return true;
-  must(hb_memcpy_h2d(ctx_, dst, src, sizeof(double) * count), "hb_memcpy_h2d");
-  return true;
+  return ok(hb_memcpy_h2d(ctx_, dst, src, sizeof(double) * count), "hb_memcpy_h2d", &healthy_);
 }
 
 bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector* grad_f, const hiopMatrixDense* Jac_c,
                                       const hiopMatrixDense* Jac_d, hiopHessianLowRank* Hess)
 {
+  if(!healthy_) return false;
   // host bookkeeping of the reference (Dx_, Dd_inv_, DhInv are still read by the inherited computeDirections and by the
   // full-KKT operator of the outer BiCGStab refinement, hiopKKTLinSys.cpp:1619-1733)
   if(!hiopKKTLinSysLowRank::update(iter, grad_f, Jac_c, Jac_d, Hess)) return false;
   nlp_->runStats.tmSolverInternal.start();
-  // Jacobian [Jc;Jd] -> device (the user callbacks write host memory, hiopNlpFormulation.cpp:1499-1533)
-  upload(dJ_, Jac_c->local_data_const(), (size_t)meq_ * n_);
-  upload(dJ_ + (size_t)meq_ * n_, Jac_d->local_data_const(), (size_t)mineq_ * n_);
-  must(hb_lowrank_set_jacobian(h_, dJ_, dJ_ + (size_t)meq_ * n_), "hb_lowrank_set_jacobian");
+  const auto t0 = std::chrono::steady_clock::now();
+  // Jacobian [Jc;Jd] -> device (the user callbacks write host memory, hiopNlpFormulation.cpp:1499-1533), but ONLY when it changed:
+  //  * the formulation re-evaluates the Jacobian of a problem declared linear / quadratic once (hiopNlpFormulation.cpp:1548-1551,
+  //    1586-1589): its evaluation counters tell whether the callback ran since the last upload;
+  //  * small Jacobians (<= 64 MB) are additionally fingerprinted, which catches constant Jacobians of problems that do not declare
+  //    themselves linear (the bundled NlpDenseConsEx1/Ex2 re-evaluate theirs every iteration with identical values).
+  const size_t jbytes = sizeof(double) * ((size_t)meq_ + mineq_) * n_;
+  const long long evals = (long long)nlp_->runStats.nEvalJac_con_eq + nlp_->runStats.nEvalJac_con_ineq;
+  bool changed = (n_jac_uploads_ == 0) || (evals != jac_evals_seen_);
+  unsigned long long hash = 0;
+  if(changed && n_jac_uploads_ > 0 && jbytes <= ((size_t)64 << 20)) {
+    hash = fnv1a(Jac_c->local_data_const(), sizeof(double) * (size_t)meq_ * n_) ^ (fnv1a(Jac_d->local_data_const(), sizeof(double) * (size_t)mineq_ * n_) * 31);
+    if(hash == jac_hash_) changed = false;
+  } else if(n_jac_uploads_ == 0 && jbytes <= ((size_t)64 << 20)) {
+    hash = fnv1a(Jac_c->local_data_const(), sizeof(double) * (size_t)meq_ * n_) ^ (fnv1a(Jac_d->local_data_const(), sizeof(double) * (size_t)mineq_ * n_) * 31);
+  }
+  jac_evals_seen_ = evals;
+  if(changed) {
+    upload(dJ_, Jac_c->local_data_const(), (size_t)meq_ * n_);
+    upload(dJ_ + (size_t)meq_ * n_, Jac_d->local_data_const(), (size_t)mineq_ * n_);
+    if(n_jac_uploads_ == 0) jac_bytes_first_ += (double)jbytes; else jac_bytes_later_ += (double)jbytes;
+    n_jac_uploads_++;
+    jac_hash_ = hash;
+    if(!ok(hb_lowrank_set_jacobian(h_, dJ_, dJ_ + (size_t)meq_ * n_), "hb_lowrank_set_jacobian", &healthy_)) return false;
+  }
   // secant memory as hiopHessianLowRank::update left it (hiopHessianLowRank.cpp:262-388)
   const int l = Hess->St_->m();
   if(l > 0) {
     upload(dSt_, Hess->St_->local_data_const(), (size_t)l * n_);
     upload(dYt_, Hess->Yt_->local_data_const(), (size_t)l * n_);
   }
-  must(hb_lowrank_set_secant(h_, l, Hess->sigma, dSt_, dYt_, l ? Hess->L_->local_data_const() : nullptr,
-                             l ? Hess->D_->local_data_const() : nullptr),
-       "hb_lowrank_set_secant");
+  if(!ok(hb_lowrank_set_secant(h_, l, Hess->sigma, dSt_, dYt_, l ? Hess->L_->local_data_const() : nullptr, l ? Hess->D_->local_data_const() : nullptr),
+         "hb_lowrank_set_secant", &healthy_))
+    return false;
   const hiopVector* blocks[8] = {iter->zl, iter->sxl, iter->zu, iter->sxu, iter->vl, iter->sdl, iter->vu, iter->sdu};
   for(int i = 0; i < 8; i++) upload(dit_[i], blocks[i]->local_data_const(), blocks[i]->get_size());
-  must(hb_lowrank_update(h_, dit_[0], dit_[1], dit_[2], dit_[3], dit_[4], dit_[5], dit_[6], dit_[7]), "hb_lowrank_update");
+  if(!healthy_) return false;
+  if(!ok(hb_lowrank_update(h_, dit_[0], dit_[1], dit_[2], dit_[3], dit_[4], dit_[5], dit_[6], dit_[7]), "hb_lowrank_update", &healthy_)) return false;
   // N and its factor depend only on the state set above: condense ONCE per update(); every preconditioner apply of the
   // outer BiCGStab then reuses it (the reference rebuilds and refactorizes N on each solveCompressed call).
+  // HB_ERR_NUMERIC (V singular / N not SPD, after the engine's own FP64 retry) is the reference's "update failed": return false and let
+  // the driver escalate (hiopAlgFilterIPM.cpp:1216-1229); the adapter stays usable.
   const int rc = hb_lowrank_condense(h_);
+  t_update_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  n_updates_++;
   nlp_->runStats.tmSolverInternal.stop();
   if(rc != HB_OK) {
     nlp_->log->printf(hovError, "hiopKKTLinSysLowRankB200::update: %s\n", hb_last_error());
@@ -180,6 +250,7 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
 bool hiopKKTLinSysLowRankB200::solveCompressed(hiopVector& rx, hiopVector& ryc, hiopVector& ryd, hiopVector& dx, hiopVector& dyc,
                                                hiopVector& dyd)
 {
+  if(!healthy_) return false;
   upload(drhs_[0], rx.local_data_const(), n_);
   upload(drhs_[1], ryc.local_data_const(), meq_);
   upload(drhs_[2], ryd.local_data_const(), mineq_);
@@ -188,20 +259,23 @@ bool hiopKKTLinSysLowRankB200::solveCompressed(hiopVector& rx, hiopVector& ryc, 
     nlp_->log->printf(hovError, "hiopKKTLinSysLowRankB200::solveCompressed: %s\n", hb_last_error());
     return false;
   }
-  if(n_) must(hb_memcpy_d2h(ctx_, dx.local_data(), dsol_[0], sizeof(double) * n_), "d2h");
-  if(meq_) must(hb_memcpy_d2h(ctx_, dyc.local_data(), dsol_[1], sizeof(double) * meq_), "d2h");
-  if(mineq_) must(hb_memcpy_d2h(ctx_, dyd.local_data(), dsol_[2], sizeof(double) * mineq_), "d2h");
+  bool a = true;
+  if(n_) a = a && ok(hb_memcpy_d2h(ctx_, dx.local_data(), dsol_[0], sizeof(double) * n_), "d2h", &healthy_);
+  if(meq_) a = a && ok(hb_memcpy_d2h(ctx_, dyc.local_data(), dsol_[1], sizeof(double) * meq_), "d2h", &healthy_);
+  if(mineq_) a = a && ok(hb_memcpy_d2h(ctx_, dyd.local_data(), dsol_[2], sizeof(double) * mineq_), "d2h", &healthy_);
   // like the reference, rx is overwritten with rx - J^T [dyc;dyd] (hiopKKTLinSys.cpp:1178)
-  if(n_) must(hb_memcpy_d2h(ctx_, rx.local_data(), drhs_[0], sizeof(double) * n_), "d2h");
-  must(hb_ctx_sync(ctx_), "hb_ctx_sync");
-  return true;
+  if(n_) a = a && ok(hb_memcpy_d2h(ctx_, rx.local_data(), drhs_[0], sizeof(double) * n_), "d2h", &healthy_);
+  a = a && ok(hb_ctx_sync(ctx_), "hb_ctx_sync", &healthy_);
+  return a;
 }
 
 bool hiopKKTLinSysLowRankB200::compute_directions_w_IR(const hiopResidual* resid, hiopIterate* dir)
 {
   const int maxit = nlp_->options->GetInteger("ir_outer_maxit");
+  if(!healthy_) return false;
   if(!ir_on_device_ || maxit <= 0) return hiopKKTLinSys::compute_directions_w_IR(resid, dir);
   nlp_->runStats.tmSolverInternal.start();
+  const auto t0 = std::chrono::steady_clock::now();
   // compound order of hiopVectorCompoundPD (hiopVectorCompoundPD.cpp:228-255)
   const hiopVector* rb[12] = {resid->rx, resid->rd, resid->ryc, resid->ryd, resid->rxl, resid->rxu, resid->rdl, resid->rdu,
                               resid->rszl, resid->rszu, resid->rsvl, resid->rsvu};
@@ -209,8 +283,11 @@ bool hiopKKTLinSysLowRankB200::compute_directions_w_IR(const hiopResidual* resid
   for(int i = 0; i < 12; i++) {
     const size_t sz = (size_t)rb[i]->get_size();
     if(!dres_[i]) {
-      must(hb_malloc(ctx_, sizeof(double) * sz, (void**)&dres_[i]), "hb_malloc(residual)");
-      must(hb_malloc(ctx_, sizeof(double) * sz, (void**)&ddir_[i]), "hb_malloc(direction)");
+      if(!ok(hb_malloc(ctx_, sizeof(double) * sz, (void**)&dres_[i]), "hb_malloc(residual)", &healthy_) ||
+         !ok(hb_malloc(ctx_, sizeof(double) * sz, (void**)&ddir_[i]), "hb_malloc(direction)", &healthy_)) {
+        nlp_->runStats.tmSolverInternal.stop();
+        return false;
+      }
     }
     upload(dres_[i], rb[i]->local_data_const(), sz);
   }
@@ -222,11 +299,18 @@ bool hiopKKTLinSysLowRankB200::compute_directions_w_IR(const hiopResidual* resid
     nlp_->runStats.tmSolverInternal.stop();
     return false;
   }
+  bool a = true;
   for(int i = 0; i < 12; i++) {
     const size_t sz = (size_t)db[i]->get_size();
-    if(sz) must(hb_memcpy_d2h(ctx_, db[i]->local_data(), ddir_[i], sizeof(double) * sz), "d2h");
+    if(sz) a = a && ok(hb_memcpy_d2h(ctx_, db[i]->local_data(), ddir_[i], sizeof(double) * sz), "d2h", &healthy_);
   }
-  must(hb_ctx_sync(ctx_), "hb_ctx_sync");
+  a = a && ok(hb_ctx_sync(ctx_), "hb_ctx_sync", &healthy_);
+  t_dirs_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  n_dirs_++;
+  if(!a) {
+    nlp_->runStats.tmSolverInternal.stop();
+    return false;
+  }
   nlp_->runStats.kkt.nIterRefinInner += info[1];
   if(info[0] != 0.0)  // the step is accepted whatever BiCGStab reports (hiopKKTLinSys.cpp:950-953)
     nlp_->log->printf(hovWarning, "BiCGStab (device) did NOT converge: flag %d after %g iters, abs res %g, rel res %g\n", (int)info[0], info[1],

@@ -12,6 +12,6 @@ class hiopKKTLinSysLowRank;
 class hiopLinSolverSymDense;
 
 hiopKKTLinSysLowRank* hiop_b200_new_lowrank_kkt(hiopNlpFormulation* nlp);
-hiopLinSolverSymDense* hiop_b200_new_symdense_solver(int n, hiopNlpFormulation* nlp, bool safe_mode);
+hiopLinSolverSymDense* hiop_b200_new_symdense_solver(int n, hiopNlpFormulation* nlp, const bool* safe_mode);
 bool hiop_b200_enabled();
 } // namespace hiop

@@ -111,6 +111,33 @@ __global__ void k_form_N(int m, int meq, int l, const double* __restrict__ C, in
   }
 }
 
+// ---- all-reduce of the symmetric C_aug as its packed upper triangle (hiopHessianLowRank.cpp:590-591 sends the full m x m buffer) ----
+__global__ void k_pack_upper(int M, const double* __restrict__ C, int ldc, double* __restrict__ tri)
+{
+  const long long tot = (long long)M * (M + 1) / 2;
+  for(long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    // row i of the upper triangle starts at i*M - i(i-1)/2
+    int i = (int)((2.0 * M + 1.0 - sqrt((2.0 * M + 1.0) * (2.0 * M + 1.0) - 8.0 * (double)e)) * 0.5);
+    while((long long)i * M - (long long)i * (i - 1) / 2 > e) i--;
+    while((long long)(i + 1) * M - (long long)(i + 1) * i / 2 <= e) i++;
+    const int j = i + (int)(e - ((long long)i * M - (long long)i * (i - 1) / 2));
+    tri[e] = C[(size_t)i * ldc + j];
+  }
+}
+__global__ void k_unpack_upper(int M, double* __restrict__ C, int ldc, const double* __restrict__ tri)
+{
+  const long long tot = (long long)M * (M + 1) / 2;
+  for(long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
+    int i = (int)((2.0 * M + 1.0 - sqrt((2.0 * M + 1.0) * (2.0 * M + 1.0) - 8.0 * (double)e)) * 0.5);
+    while((long long)i * M - (long long)i * (i - 1) / 2 > e) i--;
+    while((long long)(i + 1) * M - (long long)(i + 1) * i / 2 <= e) i++;
+    const int j = i + (int)(e - ((long long)i * M - (long long)i * (i - 1) / 2));
+    const double v = tri[e];
+    C[(size_t)i * ldc + j] = v;
+    C[(size_t)j * ldc + i] = v;
+  }
+}
+
 // ---- multi-dot: out[q] = sum_k R_q[k] * w[k] * x[k] * scale_q, q < nq rows (two-stage, deterministic) ------------------------
 // rows q < l come from S (scale sigma_s), rows q >= l from Y (scale 1). w may be null (=1).
 constexpr int MD_CH = 8;
@@ -428,18 +455,84 @@ int hess_solve(hb_lowrank* k, const double* rhs, double* x)
   return HB_OK;
 }
 
+int condense_enqueue(hb_lowrank* k, int mode);
 int condense_finish(hb_lowrank* k);
 
-int do_condense(hb_lowrank* k)
+int resolve_global_n(hb_lowrank* k)
 {
   hb_ctx* c = k->ctx;
+  if(k->n_global >= 0) return HB_OK;
+  if(c->nranks == 1) { k->n_global = k->n; return HB_OK; }
+  const double nl = (double)k->n;
+  HB_CUDA(cudaMemcpyAsync(k->stats + 2, &nl, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  HB_CHECK(hb_allreduce_sum(c, k->stats + 2, 1));
+  HB_CUDA(cudaMemcpyAsync(k->stats_host + 2, k->stats + 2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  k->n_global = (long long)(k->stats_host[2] + 0.5);
+  return HB_OK;
+}
+
+// Enqueues the whole condensation (C_aug, all-reduce, V, N, equilibrated Cholesky) without touching the host. The info words are
+// copied to pinned memory; condense_check() looks at them after a stream synchronisation.
+int do_condense_async(hb_lowrank* k)
+{
   HB_REQUIRE(k->have_update, "hb_lowrank_condense: call hb_lowrank_update first");
   HB_REQUIRE(k->J || k->m == 0, "hb_lowrank_condense: Jacobian not set");
-  const int m = k->m, l = k->l, Ma = m + 2 * l;
+  const int Ma = k->m + 2 * k->l;
   HB_CHECK(refresh_rowptr(k));
+  int mode = k->condense_mode;
+  if(mode < 0) {
+    // small systems: slicing + TMA setup do not pay off. The rule looks at the GLOBAL column count so that every rank (and every
+    // world size) takes the same kernel for the same problem.
+    HB_CHECK(resolve_global_n(k));
+    mode = (k->n_global >= 32768 && Ma >= 64) ? 8 : 0;
+  }
+  HB_CHECK(condense_enqueue(k, mode));
+  k->check_pending = true;
+  k->cond_valid = true; // optimistic: a failure is reported by the next synchronous call (hb_lowrank_check / hb_lowrank_condense)
+  return HB_OK;
+}
+
+int condense_check(hb_lowrank* k)
+{
+  hb_ctx* c = k->ctx;
+  if(!k->check_pending) return HB_OK;
+  HB_CUDA(cudaStreamSynchronize(c->stream));
+  k->check_pending = false;
+  if(k->info_host[0] != 0) {
+    k->cond_valid = false;
+    return hb_fail(HB_ERR_NUMERIC, "hb_lowrank_condense: V is singular (BFGS inner matrix)%s", "");
+  }
+  if(k->info_host[1] != 0) {
+    k->cond_valid = false;
+    snprintf(g_hb_err, sizeof(g_hb_err), "hb_lowrank_condense: condensed matrix N is not SPD (leading minor %d)", k->info_host[1]);
+    return HB_ERR_NUMERIC;
+  }
+  return HB_OK;
+}
+
+// synchronous condensation: reports breakdowns now; an int8-slice condensation chosen by the AUTO rule whose Cholesky breaks down is
+// redone once with the exact FP64 kernel (the 5e-14 |N| perturbation of the emulation can cost positive definiteness of a nearly
+// singular N late in the interior-point iteration; the reference's DPOSVX sees exact FP64 sums)
+int do_condense(hb_lowrank* k)
+{
+  HB_CHECK(do_condense_async(k));
+  int rc = condense_check(k);
+  if(rc == HB_ERR_NUMERIC && k->condense_mode < 0 && k->condense_used != 0 && k->info_host[0] == 0) {
+    HB_CHECK(condense_enqueue(k, 0));
+    k->check_pending = true;
+    k->cond_valid = true;
+    k->fallbacks++;
+    rc = condense_check(k);
+  }
+  return rc;
+}
+
+int condense_enqueue(hb_lowrank* k, int mode)
+{
+  hb_ctx* c = k->ctx;
+  const int m = k->m, l = k->l, Ma = m + 2 * l;
   if(Ma > 0) {
-    int mode = k->condense_mode;
-    if(mode < 0) mode = (k->n >= 32768 && Ma >= 64) ? 8 : 0; // small systems: slicing + TMA setup do not pay off
     k->condense_used = mode;
     if(mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
     else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, mode));
@@ -453,7 +546,17 @@ int condense_finish(hb_lowrank* k)
   hb_ctx* c = k->ctx;
   const int m = k->m, l = k->l, Ma = m + 2 * l;
   HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
-  if(Ma > 0) HB_CHECK(hb_allreduce_sum(c, k->Caug, (long long)Ma * Ma));
+  if(Ma > 0 && c->nranks > 1) {
+    // the symmetric C_aug travels as its packed upper triangle: Ma(Ma+1)/2 doubles instead of Ma^2
+    const long long tot = (long long)Ma * (Ma + 1) / 2;
+    if(!k->tri) HB_CHECK(dmalloc(&k->tri, (size_t)(k->m + 2 * k->lmax) * (k->m + 2 * k->lmax + 1) / 2));
+    const int g = (int)((tot + 255) / 256 < (long long)c->num_sms * 8 ? (tot + 255) / 256 : (long long)c->num_sms * 8);
+    k_pack_upper<<<g, 256, 0, c->stream>>>(Ma, k->Caug, Ma, k->tri);
+    HB_LAUNCHED();
+    HB_CHECK(hb_allreduce_sum(c, k->tri, tot));
+    k_unpack_upper<<<g, 256, 0, c->stream>>>(Ma, k->Caug, Ma, k->tri);
+    HB_LAUNCHED();
+  }
   if(l > 0) {
     k_build_V<<<(4 * l * l + 127) / 128, 128, 0, c->stream>>>(m, l, k->sigma, k->Caug, Ma, k->SSt, k->Ld, k->Dd_sec, k->V);
     HB_LAUNCHED();
@@ -473,13 +576,6 @@ int condense_finish(hb_lowrank* k)
     HB_CHECK(hb_dense_chol_with_inverses(c, m, k->F, m, k->info + 1, k->Finv, &k->have_finv));
   }
   HB_CUDA(cudaMemcpyAsync(k->info_host, k->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
-  HB_CUDA(cudaStreamSynchronize(c->stream));
-  if(k->info_host[0] != 0) return hb_fail(HB_ERR_NUMERIC, "hb_lowrank_condense: V is singular (BFGS inner matrix)%s", "");
-  if(k->info_host[1] != 0) {
-    snprintf(g_hb_err, sizeof(g_hb_err), "hb_lowrank_condense: condensed matrix N is not SPD (leading minor %d)", k->info_host[1]);
-    return HB_ERR_NUMERIC;
-  }
-  k->cond_valid = true;
   return HB_OK;
 }
 
@@ -495,6 +591,12 @@ int hb_lr_gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* 
 }
 int hb_lr_multidot(hb_lowrank* k, const double* w, const double* x, double sigma_s) { return multidot(k, w, x, sigma_s); }
 int hb_lr_refresh_rowptr(hb_lowrank* k) { return refresh_rowptr(k); }
+int hb_lr_global_n(hb_lowrank* k, long long* n_global)
+{
+  HB_CHECK(resolve_global_n(k));
+  *n_global = k->n_global;
+  return HB_OK;
+}
 
 extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_ineq, int l_max, hb_lowrank** out)
 {
@@ -538,7 +640,7 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv, k->Ctmp};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv, k->Ctmp, k->tri};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);
@@ -648,10 +750,22 @@ extern "C" int hb_lowrank_condense(hb_lowrank* k)
   return do_condense(k);
 }
 
+extern "C" int hb_lowrank_condense_async(hb_lowrank* k)
+{
+  HB_REQUIRE(k, "null handle");
+  return do_condense_async(k);
+}
+extern "C" int hb_lowrank_check(hb_lowrank* k)
+{
+  HB_REQUIRE(k, "null handle");
+  return condense_check(k);
+}
+extern "C" int hb_lowrank_fallback_count(hb_lowrank* k) { return k ? k->fallbacks : 0; }
+
 extern "C" int hb_lowrank_hess_solve(hb_lowrank* k, const double* rhs, double* x)
 {
   HB_REQUIRE(k && (k->n == 0 || (rhs && x)), "hb_lowrank_hess_solve: null argument");
-  if(!k->cond_valid) HB_CHECK(do_condense(k));
+  if(!k->cond_valid) HB_CHECK(do_condense_async(k));
   return hess_solve(k, rhs, x);
 }
 
@@ -661,7 +775,7 @@ extern "C" int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const doub
   HB_REQUIRE(k->n == 0 || (rx && dx), "hb_lowrank_solve_compressed: null x block");
   HB_REQUIRE((k->meq == 0 || (ryc && dyc)) && (k->mineq == 0 || (ryd && dyd)), "hb_lowrank_solve_compressed: null dual block");
   hb_ctx* c = k->ctx;
-  if(!k->cond_valid) HB_CHECK(do_condense(k));
+  if(!k->cond_valid) HB_CHECK(do_condense_async(k)); // breakdowns surface at the next synchronous call (hb_lowrank_check)
   const int m = k->m;
   // 1. dx_tmp = (H+Dx)^{-1} rx                                  hiopKKTLinSys.cpp:1146
   HB_CHECK(hess_solve(k, rx, dx));
@@ -687,6 +801,7 @@ extern "C" int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const doub
 extern "C" int hb_lowrank_last_solve_stats(hb_lowrank* k, int* n_refine, double* resid_inf)
 {
   HB_REQUIRE(k, "null handle");
+  HB_CHECK(condense_check(k));
   HB_CUDA(cudaStreamSynchronize(k->ctx->stream));
   if(n_refine) *n_refine = k->m > 0 ? (int)k->stats_host[0] : 0;
   if(resid_inf) *resid_inf = k->m > 0 ? k->stats_host[1] : 0.0;
@@ -847,6 +962,9 @@ extern "C" int hb_lowrank_kkt_system_host(hb_lowrank* k, const double* Jc_host, 
     }
     c->timing = timing_saved;
     HB_CHECK(condense_finish(k));
+    k->check_pending = true;
+    k->cond_valid = true;
+    HB_CHECK(condense_check(k));
   }
   HB_CHECK(hb_lowrank_solve_compressed(k, k->hbuf[8], k->hbuf[9], k->hbuf[10], k->hbuf[11], k->hbuf[12], k->hbuf[13]));
   if(n) HB_CUDA(cudaMemcpyAsync(dx, k->hbuf[11], sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));

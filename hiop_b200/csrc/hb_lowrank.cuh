@@ -28,6 +28,10 @@ struct hb_lowrank
   bool have_update = false, cond_valid = false, mdir_valid = false;
   int condense_mode = -1; // -1 = auto, 0 = FP64 DMMA, 6/7/8 = INT8-slice tcgen05
   int condense_used = 0;
+  long long n_global = -1; // sum of n over the ranks (the auto rule must not depend on the world size); resolved at the first condensation
+  bool check_pending = false; // an asynchronous condensation left its info words unchecked
+  int fallbacks = 0;          // times the FP64 kernel had to redo an int8-slice condensation whose Cholesky broke down
+  double* tri = nullptr;      // packed upper triangle of C_aug for the all-reduce
   // host staging (hb_lowrank_kkt_system_host)
   double* hbuf[16] = {nullptr};
   double* hJ = nullptr;
@@ -63,3 +67,5 @@ int hb_lr_gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* 
 int hb_lr_multidot(hb_lowrank* k, const double* w, const double* x, double sigma_s);
 // device table of row pointers [J rows (m); S rows (l); Y rows (l)] -> k->rowptr_dev, k->rows_aligned
 int hb_lr_refresh_rowptr(hb_lowrank* k);
+// sum of n over the ranks (resolved once, by an all-reduce, when there is a communicator)
+int hb_lr_global_n(hb_lowrank* k, long long* n_global);

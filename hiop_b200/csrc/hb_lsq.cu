@@ -57,7 +57,11 @@ extern "C" int hb_lowrank_lsq_duals(hb_lowrank* k, const double* grad_f, const d
   HB_CHECK(hb_lr_refresh_rowptr(k));
   // J J^T: rows 0..m-1 of the row-pointer table are the Jacobian rows
   int mode = k->condense_mode;
-  if(mode < 0) mode = (n >= 32768 && m >= 64) ? 8 : 0;
+  if(mode < 0) {
+    long long ng = n;
+    HB_CHECK(hb_lr_global_n(k, &ng));
+    mode = (ng >= 32768 && m >= 64) ? 8 : 0;
+  }
   if(mode == 0) HB_CHECK(hb_syrk_rows(c, m, n, k->rowptr_dev, k->rows_aligned, nullptr, M, m));
   else HB_CHECK(hb_syrk_rows_ozaki(c, m, n, k->rowptr_dev, k->rows_aligned, nullptr, M, m, mode));
   HB_CHECK(hb_allreduce_sum(c, M, (long long)m * m));

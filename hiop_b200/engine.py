@@ -334,7 +334,18 @@ class KKTLinSysLowRank:
         return int(self.ctx.L.hb_lowrank_get_condense_mode(self.h))
 
     def condense(self):
+        """synchronous: raises on a breakdown (after the FP64 retry of the AUTO mode)"""
         check(self.ctx.L.hb_lowrank_condense(self.h), "hb_lowrank_condense")
+
+    def condense_async(self):
+        check(self.ctx.L.hb_lowrank_condense_async(self.h), "hb_lowrank_condense_async")
+
+    def check(self):
+        """synchronises and reports a breakdown of an asynchronous condensation"""
+        check(self.ctx.L.hb_lowrank_check(self.h), "hb_lowrank_check")
+
+    def fallback_count(self) -> int:
+        return int(self.ctx.L.hb_lowrank_fallback_count(self.h))
 
     def solveCompressed(self, rx, ryc, ryd, dx, dyc, dyd) -> bool:
         """rx is clobbered, like in the reference (hiopKKTLinSys.cpp:1178)."""

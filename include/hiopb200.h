@@ -2,7 +2,7 @@
  *
  * Drop-in boundary: every entry point below replaces one reference interface (cited as file:line relative to
  * the LLNL/hiop tree). The library is libhiopb200.so; INTEGRATION.md shows the C++ adapter classes
- * (hiopLinSolverSymDenseB200, hiopKKTLinSysLowRankB200, hiopVectorB200) a HiOp maintainer would add on top.
+ * (hiopLinSolverSymDenseB200, hiopKKTLinSysLowRankB200, hiopHessianLowRankB200) a HiOp maintainer would add on top.
  *
  * Conventions (copied from the reference's own C interface, src/Interface/hiopInterface.h): plain pointers and
  * sizes, `int` status returns (HB_OK = 0, negative = error; hb_last_error() gives the text), no exceptions cross the
@@ -55,8 +55,9 @@ int hb_ctx_sync(hb_ctx* ctx);
 void* hb_ctx_stream(hb_ctx* ctx);
 int hb_ctx_device(hb_ctx* ctx);
 
-/* Kernel-level timing for roofline reporting: when enabled, CUDA events bracket the dominant kernel (the FP64 DMMA
- * condensation SYRK) on the context stream; hb_ctx_last_syrk_ms waits for it and returns its device duration. */
+/* Kernel-level timing for roofline reporting: when enabled, CUDA events bracket the dominant kernel of the condensation -- whichever
+ * ran: the FP64 DMMA SYRK (k_syrk_ws) or the int8-slice tcgen05 GEMM (k_oz_gemm) -- on the context stream; hb_ctx_last_syrk_ms waits
+ * for it and returns its device duration. */
 int hb_ctx_enable_timing(hb_ctx* ctx, int on);
 int hb_ctx_last_syrk_ms(hb_ctx* ctx, float* ms_host);
 
@@ -255,9 +256,17 @@ int hb_lowrank_condense(hb_lowrank* k);
  *   HB_CONDENSE_FP64_DMMA (0): exact FP64 on the DMMA pipe (mma.sync.m8n8k4.f64);
  *   6, 7, 8: INT8-slice (Ozaki) emulation on the tcgen05 tensor cores with that many 7-bit slices -- exact integer
  *   products/accumulation in TMEM, truncation of the operands 2^-41 / 2^-48 / 2^-55 relative to each row's largest entry. */
-#define HB_CONDENSE_AUTO (-1)      /* default: 8 slices on tcgen05 when n_local >= 32768 and m+2l >= 64, FP64 DMMA otherwise */
+#define HB_CONDENSE_AUTO (-1)      /* default: 8 slices on tcgen05 when the GLOBAL n (summed over the ranks) >= 32768 and m+2l >= 64, FP64 DMMA otherwise */
 #define HB_CONDENSE_FP64_DMMA 0
 int hb_lowrank_set_condense_mode(hb_lowrank* k, int mode);
+/* hb_lowrank_condense is synchronous: it returns HB_ERR_NUMERIC when V is singular or N is not numerically SPD. In AUTO mode an
+ * int8-slice condensation whose Cholesky breaks down is first redone with the exact FP64 kernel (hb_lowrank_fallback_count counts
+ * these). hb_lowrank_condense_async only enqueues the work (no host synchronisation; this is also what an implicit condensation
+ * inside hb_lowrank_solve_compressed does); a breakdown is then reported by hb_lowrank_check / hb_lowrank_last_solve_stats, the next
+ * calls that synchronise. */
+int hb_lowrank_condense_async(hb_lowrank* k);
+int hb_lowrank_check(hb_lowrank* k);
+int hb_lowrank_fallback_count(hb_lowrank* k);
 /* the mode the last hb_lowrank_condense actually used (0, 6, 7 or 8) */
 int hb_lowrank_get_condense_mode(hb_lowrank* k);
 /* solveCompressed(rx,ryc,ryd -> dx,dyc,dyd) (hiopKKTLinSys.cpp:1110-1190) incl. the residual-driven refinement of

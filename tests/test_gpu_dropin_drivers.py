@@ -103,3 +103,65 @@ def test_mds1_iterate_sequence(linsol):
         os.environ.pop("HIOP_B200_LINSOL", None)
     assert "selfcheck passed" in out
     assert worst <= 1e-5, worst
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# parametrised-m dense-constraints problem (oracle/drivers/NlpDenseConsExM.cpp: this repo's generalisation of NlpDenseConsEx1, SURVEY
+# section 0 item 4): the bundled drivers have m <= 4, so only here does the default int8-slice condensation run inside the interior-point
+# loop (AUTO switches to it for global n >= 32768 and m + 2l >= 64). Reference vs HB_CONDENSE=dmma vs HB_CONDENSE=oz8 under the 1e-5 rule.
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _run_env(exe, args, env_extra):
+    path = os.path.join(REF, exe)
+    if not os.path.exists(path):
+        pytest.skip(f"{exe} not built (oracle/_ref travels from the build container)")
+    env = dict(os.environ)
+    for k in ("HIOP_B200", "HB_CONDENSE", "HIOP_B200_STATS"):
+        env.pop(k, None)
+    env.update(env_extra)
+    p = subprocess.run([path] + args, capture_output=True, text=True, env=env, timeout=900)
+    table = [[float(x) for x in m.groups()] for m in (ROW.match(line) for line in p.stdout.splitlines()) if m]
+    return p.returncode, p.stdout, p.stderr, table
+
+
+def _tables_agree(tab_b, tab_r):
+    assert len(tab_r) > 3 and len(tab_b) == len(tab_r), (len(tab_b), len(tab_r))
+    worst = 0.0
+    for a, b in zip(tab_b, tab_r):
+        assert a[0] == b[0]
+        assert abs(a[1] - b[1]) <= 1e-7 * max(1.0, abs(b[1])), (a, b)
+        worst = max(worst, max(abs(a[j] - b[j]) for j in (2, 3, 4, 5, 6)))
+    return worst
+
+
+@pytest.mark.parametrize("n,m", [(1000, 50), (33000, 64), (33000, 128)])
+def test_exM_iterate_sequence_both_condensation_kernels(n, m):
+    rc_r, out_r, _, tab_r = _run_env("exM_b200.exe", [str(n), str(m)], {})
+    assert rc_r == 0, out_r[-1500:]
+    for mode in ("dmma", "oz8", None):      # None = AUTO (int8 slices at the two large sizes, FP64 DMMA at n = 1000)
+        env = {"HIOP_B200": "1"}
+        if mode:
+            env["HB_CONDENSE"] = mode
+        rc_b, out_b, err_b, tab_b = _run_env("exM_b200.exe", [str(n), str(m)], env)
+        assert rc_b == 0, (mode, out_b[-1500:], err_b[-500:])
+        worst = _tables_agree(tab_b, tab_r)
+        assert worst <= 1e-5, (mode, worst)
+
+
+def test_exM_jacobian_is_uploaded_once():
+    """zero Jacobian bytes after the first upload: (a) the problem declares itself linear -> HiOp evaluates the Jacobian once and the adapter
+    sees an unchanged evaluation counter; (b) it does not -> the (small) Jacobian is fingerprinted and found unchanged."""
+    for extra in (["-linear"], []):
+        rc, out, err, tab = _run_env("exM_b200.exe", ["4000", "60"] + extra, {"HIOP_B200": "1", "HIOP_B200_STATS": "1"})
+        assert rc == 0, out[-1500:]
+        m = re.search(r"Jacobian uploads (\d+) \(first (\d+) bytes, after the first (\d+) bytes\), KKT update\+condense ([\d.]+) ms/it", err)
+        assert m, err[-800:]
+        assert int(m.group(1)) == 1 and int(m.group(2)) == 8 * 60 * 4000 and int(m.group(3)) == 0, m.groups()
+        assert len(tab) > 5
+
+
+def test_speculative_mode_falls_back_to_bunch_kaufman():
+    """linsol_mode=speculative factorizes with LDL^T without pivoting until HiOp switches safe mode on; the adapter reads the KKT object's
+    safe-mode flag at every matrixChanged(), so the stability fallback (MagmaNopiv -> MagmaBuKa in the reference) is kept. The driver must
+    reach the same optimum with both settings."""
+    rc0, out0, _, tab0 = _run_env("mds1_b200.exe", ["400", "100", "0", "-selfcheck"], {"HIOP_B200": "1"})
+    assert rc0 == 0 and "selfcheck passed" in out0, out0[-1000:]

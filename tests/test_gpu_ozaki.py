@@ -84,3 +84,76 @@ def test_ozaki_rows_with_huge_dynamic_range(ctx):
     assert err.max() <= 1e-12, err.max()
     k0.close()
     k1.close()
+
+
+def _oracle_N(P):
+    Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P.zl, P.sxl, P.zu, P.sxu, P.ixl, P.ixu, P.vl, P.sdl, P.vu, P.sdu, P.idl, P.idu, P.sigma)
+    st = ko.QnState(P.Jc, P.Jd, DhInv, Dd_inv, P.St, P.Yt, P.L, P.D, P.sigma)
+    N, W0, S1, Y1 = ko.condense(st)
+    return N, DhInv
+
+
+def test_oz8_against_oracle_at_scale_adversarial_scaling(ctx):
+    """k_oz_gemm<8> against the ORACLE's restatement of symMatTimesInverseTimesMatTrans (src/Optimization/hiopHessianLowRank.cpp:549-630,
+    the scalar triple loops :1079-1154; oracle/kkt_oracle.c is pinned to the compiled reference by tests/test_oracle_vs_ref.py) at a size
+    with several K chunks (n = 200001 > 3 x 65535), an odd n, a 5 x 3 tile grid, DhInv spanning 16 decades and Jacobian rows spanning 12
+    decades. Error model of the slicing: relative to the row scales, i.e. to sqrt(N_ii N_jj)."""
+    n, m, l = 200001, 300, 4
+    P = synth.make_qn_problem(n, m, l, seed=4242)
+    r = np.random.default_rng(7)
+    # Dx = zl/sxl in [1, 1e16]  ->  DhInv = 1/(sigma + Dx) spans 16 decades
+    P.sxl[:] = 10.0 ** r.uniform(-8.0, 0.0, n)
+    P.zl[:] = 10.0 ** r.uniform(0.0, 8.0, n)
+    rowscale = 10.0 ** (12.0 * np.arange(m) / (m - 1) - 6.0)
+    P.Jc *= rowscale[:P.m_eq, None]
+    P.Jd *= rowscale[P.m_eq:, None]
+    No, DhInv = _oracle_N(P)
+    assert DhInv.max() / DhInv.min() > 1e15
+    scale = np.sqrt(np.outer(np.abs(np.diag(No)), np.abs(np.diag(No))))
+    for mode, tol in ((8, 2e-12), (0, 1e-12)):
+        k, T = _setup(ctx, P, mode)
+        k.condense()
+        assert k.condense_mode_used() == mode
+        Ng = k.N()
+        err = (np.abs(Ng - No) / scale).max()
+        assert err <= tol, (mode, err)
+        k.close()
+
+
+def test_auto_mode_uses_global_n_and_falls_back_to_fp64(ctx):
+    """AUTO picks the kernel from the global column count (identical on every rank / world size) and, when the Cholesky of an
+    int8-slice condensation breaks down, redoes it once with the exact FP64 kernel before reporting failure."""
+    # (1) near-singular N: two identical equality rows + a tiny inequality regularisation. Exact FP64 keeps N (barely) positive definite or
+    #     not -- either way AUTO must end where the FP64 mode ends, and count the retry when the int8 attempt failed.
+    n, m, l = 40000, 70, 2
+    P = synth.make_qn_problem(n, m, l, seed=99)
+    P.Jc[1, :] = P.Jc[0, :] * (1.0 + 1e-15)
+    outcomes = {}
+    for mode in (0, -1):
+        k, T = _setup(ctx, P, mode)
+        try:
+            k.condense()
+            outcomes[mode] = ("ok", k.condense_mode_used(), k.fallback_count())
+        except Exception as e:  # noqa: BLE001
+            outcomes[mode] = ("fail", k.condense_mode_used(), k.fallback_count())
+        k.close()
+    assert outcomes[-1][0] == outcomes[0][0], outcomes
+    if outcomes[-1][2] > 0:
+        assert outcomes[-1][1] == 0           # the retry ran the FP64 kernel
+    # (2) s, z down to 1e-10 (late interior-point iterates): AUTO (int8 slices) still delivers the direction within 1e-8
+    P2 = synth.make_qn_problem(50000, 80, 4, seed=5)
+    r = np.random.default_rng(3)
+    P2.sxl[:] = 10.0 ** r.uniform(-10.0, 0.0, P2.n)
+    P2.zl[:] = 10.0 ** r.uniform(-10.0, 0.0, P2.n)
+    k, T = _setup(ctx, P2, -1)
+    k.condense()
+    assert k.condense_mode_used() == 8
+    dx, dyc, dyd = [ctx.zeros(s) for s in (P2.n, P2.m_eq, P2.m_ineq)]
+    assert k.solveCompressed(ctx.to_device(P2.rx), T["ryc"], T["ryd"], dx, dyc, dyd)
+    k.check()
+    Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P2.zl, P2.sxl, P2.zu, P2.sxu, P2.ixl, P2.ixu, P2.vl, P2.sdl, P2.vu, P2.sdu, P2.idl, P2.idu, P2.sigma)
+    st = ko.QnState(P2.Jc, P2.Jd, DhInv, Dd_inv, P2.St, P2.Yt, P2.L, P2.D, P2.sigma)
+    dxo, dyco, dydo, _ = ko.solve_compressed(st, P2.rx, P2.ryc, P2.ryd)
+    assert np.abs(dx.cpu().numpy() - dxo).max() <= 1e-8 * np.abs(dxo).max()
+    assert np.abs(dyd.cpu().numpy() - dydo).max() <= 1e-8 * max(1.0, np.abs(dydo).max())
+    k.close()
