@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libhiopb200.so")
+SO_PATH = os.environ.get("HIOPB200_SO") or os.path.join(_HERE, "libhiopb200.so")   # HIOPB200_SO: A/B runs of tools/ against another build
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "hiopb200.h")
 
 HB_OK = 0

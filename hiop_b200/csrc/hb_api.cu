@@ -44,6 +44,7 @@ extern "C" int hb_ctx_destroy(hb_ctx* c)
   if(!c) return HB_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if(c->oz_state && c->oz_free) c->oz_free(c->oz_state);
   if(c->ws) cudaFree(c->ws);
   if(c->ev_syrk0) { cudaEventDestroy(c->ev_syrk0); cudaEventDestroy(c->ev_syrk1); }
   cudaFree(c->red_dev);

@@ -69,6 +69,9 @@ struct hb_ctx
   bool timing = false;
   cudaEvent_t ev_syrk0 = nullptr, ev_syrk1 = nullptr;
   bool syrk_timed = false;
+  // per-context state of the int8-slice condensation (hb_ozaki.cu): slice buffer, exponents, tensor maps, work list
+  void* oz_state = nullptr;
+  void (*oz_free)(void*) = nullptr;
   // NCCL
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;

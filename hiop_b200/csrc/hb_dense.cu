@@ -835,11 +835,17 @@ int hb_dense_equilibrate(hb_ctx* c, int N, const double* Nfull, int ldn, double*
 
 // SPD factorization that also keeps the 16 x 16 diagonal inverses for the cooperative solve (invd: HB_CHOL_INV_DOUBLES(N) doubles);
 // *have_inv tells whether they were produced (small / large N use the multi-launch path and the one-CTA solve)
+static hb_big g_chol_big[16]; // look-ahead state (panel stream, scratch) of the large condensed systems, one per device
+
 int hb_dense_chol_with_inverses(hb_ctx* c, int N, double* A, int lda, int* info_dev, double* invd, bool* have_inv)
 {
   *have_inv = false;
   HB_CHECK(hb_dense_chol_coop(c, N, A, lda, info_dev, invd, have_inv));
   if(*have_inv) return HB_OK;
+  // beyond the single-launch cooperative kernel: the look-ahead Cholesky of hb_dense_big.cu (config 4: m = 4000 per condensed system)
+  if(N > 2048 && (lda & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0 && c->device < 16) {
+    HB_CHECK(hb_big_factor(c, &g_chol_big[c->device], N, A, lda, false, info_dev));
+  } else
   HB_CHECK(hb_dense_factor_blocked(c, N, A, lda, false, nullptr, info_dev));
   if(N > 64 && invd && hb_dense_coop_available(c)) { // large N: multi-launch factor, but the solve can still be cooperative
     HB_CHECK(hb_dense_chol_diag_inverses(c, N, A, lda, invd));

@@ -95,6 +95,8 @@ __global__ void k_stack(int me, int mi, const double* __restrict__ a, const doub
   else if(i < me + mi) out[i] = b[i - me];
 }
 
+constexpr int KRY_EXTRA = 4 * 2048 + 64;
+
 int ensure_ws(hb_lowrank* k, const Layout& L, int nvec)
 {
   if(!k->kry) {
@@ -102,7 +104,8 @@ int ensure_ws(hb_lowrank* k, const Layout& L, int nvec)
       cudaGetLastError();
       return hb_fail(HB_ERR_ALLOC, "BiCGStab workspace allocation failed%s", "");
     }
-    if(cudaMalloc(&k->kry_m, sizeof(double) * (size_t)(2 * k->m + 2)) != cudaSuccess) {
+    // 2 m-vectors + the device scalars and per-CTA partial sums of the recurrence (KRY_EXTRA doubles)
+    if(cudaMalloc(&k->kry_m, sizeof(double) * (size_t)(2 * k->m + 2 + KRY_EXTRA)) != cudaSuccess) {
       cudaGetLastError();
       return hb_fail(HB_ERR_ALLOC, "BiCGStab m-workspace%s", "");
     }
@@ -192,6 +195,110 @@ int scatter(hb_lowrank* k, const Layout& L, const double* buf, double* const* pa
 
 constexpr int NVEC = 11; // b, xk, xmin, res, pk, ph, v, sk, t, rt, io
 
+// ---------------------------------------------------------------------------------------------------------------------------------
+// Device-driven recurrence. The scalars of BiCGStab (rho, alpha, omega, beta, the norms) live in a small device block; the vector
+// updates read them there, every group of inner products of a half-iteration is ONE pass (fused with the vector update that produces
+// the vector being measured), and the host looks at the scalars once per half-iteration to take the reference's exit decisions
+// (hiopKrylovSolver.cpp:470-660) -- two stream synchronisations per iteration instead of twelve, 5 passes over the compound vectors
+// instead of 14. With a communicator each group is one all-reduce of 4 doubles.
+// ---------------------------------------------------------------------------------------------------------------------------------
+enum { SC_RHO = 0, SC_RHO1, SC_ALPHA, SC_OMEGA, SC_BETA, SC_RTV, SC_NPH2, SC_NXK2, SC_NRM2, SC_TT, SC_TS, SC_BAD, SC_NEWRHO, SC_COUNT = 16 };
+enum { KM_P = 0, KM_A, KM_B, KM_D3, KM_D4 };
+constexpr int KT = 256;
+
+// One fused pass over the compound vectors. `len` elements are updated, the inner products run over the first `red_len` only (ranks
+// other than 0 leave the replicated m-sized tail out of the sums). partial[blockIdx.x*4 + q].
+template <int MODE>
+__global__ void __launch_bounds__(KT)
+k_kry_pass(long long len, long long red_len, const double* __restrict__ sc, int first, double* __restrict__ xk, double* __restrict__ pk,
+           const double* __restrict__ ph, double* __restrict__ r, const double* __restrict__ v, double* __restrict__ sk, const double* __restrict__ t,
+           const double* __restrict__ rt, double* __restrict__ partial)
+{
+  __shared__ double sm[KT / 32];
+  const bool bad = sc[SC_BAD] != 0.0;
+  const double alpha = sc[SC_ALPHA], omega = sc[SC_OMEGA], beta = sc[SC_BETA];
+  double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+  const long long stride = (long long)gridDim.x * KT;
+  for(long long i = (long long)blockIdx.x * KT + threadIdx.x; i < len; i += stride) {
+    const bool in = i < red_len;
+    if(MODE == KM_P) {
+      if(!bad) pk[i] = first ? r[i] : fma(1.0, r[i], fma(-omega, v[i], pk[i]) * beta); // axpy(pk,-omega,v); scale(beta); axpy(pk,1,r)
+    } else if(MODE == KM_A) {
+      if(!bad) {
+        xk[i] = fma(alpha, ph[i], xk[i]);
+        const double s = fma(-alpha, v[i], r[i]);
+        sk[i] = s;
+        if(in) d0 += s * s;
+      }
+    } else if(MODE == KM_B) {
+      if(!bad) {
+        xk[i] = fma(omega, ph[i], xk[i]);
+        const double rr = fma(-omega, t[i], sk[i]);
+        r[i] = rr;
+        if(in) { d0 += rr * rr; d1 += rt[i] * rr; }
+      }
+    } else if(MODE == KM_D3) {
+      if(in) { d0 += rt[i] * v[i]; d1 += ph[i] * ph[i]; d2 += xk[i] * xk[i]; }
+    } else {
+      if(in) { const double tv = t[i]; d0 += tv * tv; d1 += tv * sk[i]; d2 += ph[i] * ph[i]; d3 += xk[i] * xk[i]; }
+    }
+  }
+  if(MODE == KM_P) return;
+  const double r0 = hb_block_sum<KT>(d0, sm), r1 = hb_block_sum<KT>(d1, sm), r2 = hb_block_sum<KT>(d2, sm), r3 = hb_block_sum<KT>(d3, sm);
+  if(threadIdx.x == 0) {
+    partial[blockIdx.x * 4 + 0] = r0; partial[blockIdx.x * 4 + 1] = r1; partial[blockIdx.x * 4 + 2] = r2; partial[blockIdx.x * 4 + 3] = r3;
+  }
+}
+// sums[q] = sum over the per-CTA partials, fixed order (one warp per q)
+__global__ void __launch_bounds__(128)
+k_kry_final(int np, const double* __restrict__ partial, double* __restrict__ sums)
+{
+  const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double a = 0.0;
+  for(int i = lane; i < np; i += 32) a += partial[i * 4 + q];
+  a = hb_warp_sum(a);
+  if(lane == 0) sums[q] = a;
+}
+// the scalar recurrences and breakdown guards (hiopKrylovSolver.cpp:476-486, 505-513, 576-590), one thread
+__global__ void k_kry_scalars(int op, int ii, double* __restrict__ sc, const double* __restrict__ sums)
+{
+  if(threadIdx.x != 0 || blockIdx.x != 0) return;
+  if(op == 0) { // start of an iteration: rho1 <- rho, rho <- <rt, r>, beta
+    sc[SC_RHO1] = sc[SC_RHO];
+    const double rho = sc[SC_NEWRHO];
+    sc[SC_RHO] = rho;
+    if(rho == 0.0 || fabs(rho) > 1e40) sc[SC_BAD] = 1.0;
+    if(ii > 0) {
+      const double beta = rho / sc[SC_RHO1] * (sc[SC_ALPHA] / sc[SC_OMEGA]);
+      sc[SC_BETA] = beta;
+      if(beta == 0.0 || fabs(beta) > 1e40) sc[SC_BAD] = 1.0;
+    }
+  } else if(op == 1) { // alpha
+    sc[SC_RTV] = sums[0]; sc[SC_NPH2] = sums[1]; sc[SC_NXK2] = sums[2];
+    if(sc[SC_BAD] == 0.0) {
+      const double rtv = sums[0];
+      if(rtv == 0.0 || fabs(rtv) > 1e40) sc[SC_BAD] = 1.0;
+      const double alpha = sc[SC_RHO] / rtv;
+      sc[SC_ALPHA] = alpha;
+      if(fabs(alpha) > 1e20) sc[SC_BAD] = 1.0;
+    }
+  } else if(op == 2) { // ||sk||^2
+    sc[SC_NRM2] = sums[0];
+  } else if(op == 3) { // omega
+    sc[SC_TT] = sums[0]; sc[SC_TS] = sums[1]; sc[SC_NPH2] = sums[2]; sc[SC_NXK2] = sums[3];
+    if(sc[SC_BAD] == 0.0) {
+      const double tt = sums[0];
+      if(tt == 0.0 || fabs(tt) > 1e20) sc[SC_BAD] = 1.0;
+      const double omega = sums[1] / tt;
+      sc[SC_OMEGA] = omega;
+      if(fabs(omega) > 1e20) sc[SC_BAD] = 1.0;
+    }
+  } else { // ||r||^2 and the next rho
+    sc[SC_NRM2] = sums[0];
+    sc[SC_NEWRHO] = sums[1];
+  }
+}
+
 } // namespace
 
 extern "C" int hb_lowrank_kkt_full_times_vec(hb_lowrank* k, const double* const* x, double* const* y)
@@ -251,40 +358,69 @@ extern "C" int hb_lowrank_compute_directions_w_ir(hb_lowrank* k, const double* c
     return finish(xk);
   }
   HB_CHECK(cv.copy(rt, r));
-  double normrmin = normr, rho = 1.0, omega = 1.0, alpha = 0.0, rho1;
+  double normrmin = normr;
   int stagsteps = 0, moresteps = 0;
   const double eps = std::numeric_limits<double>::epsilon();
   const int maxmsteps = 100, maxstagsteps = 3;
   bool returned_xk = false; // the two "tol is too small" exits copy xk into b before the closing min-residual test (:546, :623)
+  // device scalar block + per-CTA partial sums live behind the m-workspace; the host mirror is the pinned stats buffer of the handle
+  hb_ctx* c = k->ctx;
+  int kg = egrid(c, L.total);
+  if(kg > 2048) kg = 2048;
+  double* partial = k->kry_m + (size_t)(2 * k->m + 2); // (the context workspace is used by the kernels inside precond / K)
+  double* sc = partial + (size_t)kg * 4;
+  double* sums = sc + SC_COUNT;
+  double sc_host[SC_COUNT];
+  const long long red_len = cv.red_len();
+  auto group = [&](int op, int ii_) -> int { // partials -> 4 sums (all-reduced) -> scalar program
+    k_kry_final<<<1, 128, 0, c->stream>>>(kg, partial, sums);
+    HB_LAUNCHED();
+    HB_CHECK(hb_allreduce_sum(c, sums, 4));
+    k_kry_scalars<<<1, 32, 0, c->stream>>>(op, ii_, sc, sums);
+    HB_LAUNCHED();
+    return HB_OK;
+  };
+  auto poll = [&]() -> int {
+    HB_CUDA(cudaMemcpyAsync(sc_host, sc, sizeof(double) * SC_COUNT, cudaMemcpyDeviceToHost, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    return HB_OK;
+  };
+  {
+    // rho = 1, omega = 1, alpha = 0 (hiopKrylovSolver.cpp:466-468); the first <rt, r> = ||r||^2 is already known
+    double init[SC_COUNT] = {0};
+    init[SC_RHO] = 1.0; init[SC_OMEGA] = 1.0; init[SC_NEWRHO] = 0.0;
+    HB_CUDA(cudaMemcpyAsync(sc, init, sizeof(double) * SC_COUNT, cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream)); // init[] is a stack array
+    double rho0;
+    HB_CHECK(cv.dot(rt, r, &rho0));
+    HB_CUDA(cudaMemcpyAsync(sc + SC_NEWRHO, &rho0, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+  }
   int ii = 0;
   for(; ii < maxit; ++ii) {
-    rho1 = rho;
-    HB_CHECK(cv.dot(rt, r, &rho));
-    if(rho == 0.0 || std::fabs(rho) > 1e40) { flag = 4; iter = ii + 1 - 0.5; break; }
-    if(ii == 0) {
-      HB_CHECK(cv.copy(pk, r));
-    } else {
-      const double beta = rho / rho1 * (alpha / omega);
-      if(beta == 0.0 || std::fabs(beta) > 1e40) { flag = 4; iter = ii + 1 - 0.5; break; }
-      HB_CHECK(cv.axpy(pk, -omega, v));
-      HB_CHECK(cv.scale(pk, beta));
-      HB_CHECK(cv.axpy(pk, 1.0, r));
-    }
+    // ---------------- first half: p, ph = M^-1 p, v = K ph, alpha, x += alpha ph, s = r - alpha v ----------------
+    k_kry_scalars<<<1, 32, 0, c->stream>>>(0, ii, sc, sums);
+    HB_LAUNCHED();
+    k_kry_pass<KM_P><<<kg, KT, 0, c->stream>>>(L.total, red_len, sc, ii == 0 ? 1 : 0, xk, pk, ph, r, v, sk, t, rt, partial);
+    HB_LAUNCHED();
     HB_CHECK(precond(k, L, ph, pk));
     HB_CHECK(full_times_vec(k, L, v, ph));
-    double rtv;
-    HB_CHECK(cv.dot(rt, v, &rtv));
-    if(rtv == 0.0 || std::fabs(rtv) > 1e40) { flag = 4; iter = ii + 1 - 0.5; break; }
-    alpha = rho / rtv;
-    if(std::fabs(alpha) > 1e20) { flag = 4; iter = ii + 1 - 0.5; break; }
-    double nph, nxk;
-    HB_CHECK(cv.nrm2(ph, &nph));
-    HB_CHECK(cv.nrm2(xk, &nxk));
-    if(nph * std::fabs(alpha) < eps * nxk) stagsteps++; else stagsteps = 0;
-    HB_CHECK(cv.axpy(xk, alpha, ph));
-    HB_CHECK(cv.copy(sk, r));
-    HB_CHECK(cv.axpy(sk, -alpha, v));
-    HB_CHECK(cv.nrm2(sk, &normr));
+    k_kry_pass<KM_D3><<<kg, KT, 0, c->stream>>>(L.total, red_len, sc, 0, xk, pk, ph, r, v, sk, t, rt, partial);
+    HB_LAUNCHED();
+    HB_CHECK(group(1, ii));
+    k_kry_pass<KM_A><<<kg, KT, 0, c->stream>>>(L.total, red_len, sc, 0, xk, pk, ph, r, v, sk, t, rt, partial);
+    HB_LAUNCHED();
+    HB_CHECK(group(2, ii));
+    HB_CHECK(poll());
+    {
+      const double rho = sc_host[SC_RHO], beta = sc_host[SC_BETA], rtv = sc_host[SC_RTV], alpha = sc_host[SC_ALPHA];
+      if(rho == 0.0 || std::fabs(rho) > 1e40) { flag = 4; iter = ii + 1 - 0.5; break; }
+      if(ii > 0 && (beta == 0.0 || std::fabs(beta) > 1e40)) { flag = 4; iter = ii + 1 - 0.5; break; }
+      if(rtv == 0.0 || std::fabs(rtv) > 1e40) { flag = 4; iter = ii + 1 - 0.5; break; }
+      if(std::fabs(alpha) > 1e20) { flag = 4; iter = ii + 1 - 0.5; break; }
+      if(std::sqrt(sc_host[SC_NPH2]) * std::fabs(alpha) < eps * std::sqrt(sc_host[SC_NXK2])) stagsteps++; else stagsteps = 0;
+      normr = std::sqrt(sc_host[SC_NRM2]);
+    }
     abs_resid = normr;
     if(normr <= tolb || stagsteps >= maxstagsteps || moresteps) {
       HB_CHECK(cv.resid(sk, b, xk));
@@ -297,21 +433,23 @@ extern "C" int hb_lowrank_compute_directions_w_ir(hb_lowrank* k, const double* c
     if(stagsteps >= maxstagsteps) { iter = ii + 1 - 0.5; flag = 3; break; }
     if(abs_resid < normrmin) { normrmin = abs_resid; HB_CHECK(cv.copy(xmin, xk)); imin = ii + 1 - 0.5; }
 
+    // ---------------- second half: ph = M^-1 s, t = K ph, omega, x += omega ph, r = s - omega t, next rho ----------------
     HB_CHECK(precond(k, L, ph, sk));
     HB_CHECK(full_times_vec(k, L, t, ph));
-    double tt, ts;
-    HB_CHECK(cv.dot(t, t, &tt));
-    if(tt == 0.0 || std::fabs(tt) > 1e20) { iter = ii + 1; flag = 4; break; }
-    HB_CHECK(cv.dot(t, sk, &ts));
-    omega = ts / tt;
-    if(std::fabs(omega) > 1e20) { iter = ii + 1; flag = 4; break; }
-    HB_CHECK(cv.nrm2(ph, &nph));
-    HB_CHECK(cv.nrm2(xk, &nxk));
-    if(nph * std::fabs(omega) < eps * nxk) stagsteps++; else stagsteps = 0;
-    HB_CHECK(cv.axpy(xk, omega, ph));
-    HB_CHECK(cv.copy(r, sk));
-    HB_CHECK(cv.axpy(r, -omega, t));
-    HB_CHECK(cv.nrm2(r, &normr));
+    k_kry_pass<KM_D4><<<kg, KT, 0, c->stream>>>(L.total, red_len, sc, 0, xk, pk, ph, r, v, sk, t, rt, partial);
+    HB_LAUNCHED();
+    HB_CHECK(group(3, ii));
+    k_kry_pass<KM_B><<<kg, KT, 0, c->stream>>>(L.total, red_len, sc, 0, xk, pk, ph, r, v, sk, t, rt, partial);
+    HB_LAUNCHED();
+    HB_CHECK(group(4, ii));
+    HB_CHECK(poll());
+    {
+      const double tt = sc_host[SC_TT], omega = sc_host[SC_OMEGA];
+      if(tt == 0.0 || std::fabs(tt) > 1e20) { iter = ii + 1; flag = 4; break; }
+      if(std::fabs(omega) > 1e20) { iter = ii + 1; flag = 4; break; }
+      if(std::sqrt(sc_host[SC_NPH2]) * std::fabs(omega) < eps * std::sqrt(sc_host[SC_NXK2])) stagsteps++; else stagsteps = 0;
+      normr = std::sqrt(sc_host[SC_NRM2]);
+    }
     abs_resid = normr;
     if(normr <= tolb || stagsteps >= maxstagsteps || moresteps) {
       HB_CHECK(cv.resid(r, b, xk));
@@ -320,6 +458,11 @@ extern "C" int hb_lowrank_compute_directions_w_ir(hb_lowrank* k, const double* c
       if(stagsteps >= maxstagsteps && moresteps == 0) stagsteps = 0;
       moresteps++;
       if(moresteps >= maxmsteps) { returned_xk = true; flag = 3; iter = ii + 1; break; }
+      // r was replaced by the true residual: the next rho must be taken against it
+      double rho_next;
+      HB_CHECK(cv.dot(rt, r, &rho_next));
+      HB_CUDA(cudaMemcpyAsync(sc + SC_NEWRHO, &rho_next, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      HB_CUDA(cudaStreamSynchronize(c->stream));
     }
     if(abs_resid < normrmin) { normrmin = abs_resid; HB_CHECK(cv.copy(xmin, xk)); imin = ii + 1; }
     if(stagsteps >= maxstagsteps) { iter = ii + 1 - 0.5; flag = 3; break; }

@@ -418,16 +418,31 @@ struct OzState
   int2* d_tiles = nullptr;
   CUtensorMap mapA, mapB;
 };
-OzState g_oz[16];
+// one state per CONTEXT (it used to be per device: two contexts on one GPU would have shared the slice buffer across their streams)
+void oz_state_free(void* p)
+{
+  OzState* st = static_cast<OzState*>(p);
+  if(!st) return;
+  cudaFree(st->Q); cudaFree(st->sd); cudaFree(st->mx); cudaFree(st->e); cudaFree(st->d_items); cudaFree(st->d_tiles);
+  delete st;
+}
+OzState& oz_state(hb_ctx* c)
+{
+  if(!c->oz_state) {
+    c->oz_state = new OzState;
+    c->oz_free = oz_state_free;
+  }
+  return *static_cast<OzState*>(c->oz_state);
+}
 
 template <int S>
 int launch_gemm(hb_ctx* c, OzState& st, int chunk_blocks, double* partial)
 {
   const size_t smem = OzCfg<S>::SMEM;
-  static bool attr = false;
-  if(!attr) {
+  static bool attr[16] = {false}; // function attributes are per device
+  if(c->device >= 16 || !attr[c->device]) {
     HB_CUDA(cudaFuncSetAttribute(k_oz_gemm<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
+    if(c->device < 16) attr[c->device] = true;
   }
   const int G = st.n_items < c->num_sms ? st.n_items : c->num_sms;
   k_oz_gemm<S><<<G, OZ_THREADS, smem, c->stream>>>(st.mapA, st.mapB, st.d_items, st.n_items, chunk_blocks, partial);
@@ -451,7 +466,7 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
     HB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&g_encode, cudaEnableDefault, &qres));
     if(!g_encode) return hb_fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver%s", "");
   }
-  OzState& st = g_oz[c->device];
+  OzState& st = oz_state(c);
   const int Mpad = ((M + TM - 1) / TM) * TM;
   const long long Kpad = ((K + KS - 1) / KS) * KS;
   const size_t qbytes = (size_t)S * Mpad * Kpad;
