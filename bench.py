@@ -507,6 +507,17 @@ def run_engine(args):
         ctx.sync()
         kkt_resid_other = independent_kkt_residual(torch, dist, world, T, 1.0, dx, dyc, dyd)
         set_mode(args.condense)
+        # ---- per-rank phase timeline of ONE extra step (events recorded inside the library; outside the timed region) ----
+        for _ in range(2):
+            step()
+        barrier()
+        ctx.phase_timeline(True)
+        step()
+        tl = ctx.phase_timeline(False)
+        timeline = [tl]
+        if world > 1:
+            timeline = [None] * world
+            dist.all_gather_object(timeline, tl)
 
         # ---- end to end through the host-buffer entry point (public API a HiOp adapter calls when mem_space is host) ----
         e2e = None
@@ -607,6 +618,7 @@ def run_engine(args):
                        "l2": f"J is {8e-9 * m * n_local:.1f} GB per GPU, far larger than the 126 MB L2; no flush needed",
                        "refinement_steps_last": main["nref"], "residual_inf_last": main["resid"],
                        "kkt_residual_rel_independent_operators": kkt_resid_rel,
+                       "timeline_ms_per_rank": [{q: round(v, 4) for q, v in t.items()} for t in timeline],
                        "kkt_residual_note": "max-norm residual of the compressed 3-block KKT system over max-norm rhs, evaluated with torch FP64 matmuls and a "
                                             "compact-BFGS operator assembled in bench.py (no hiop_b200 kernel, not the condensed matrix); gate 1e-8"},
             "clocks": main["clocks"], "gpu_launches": main["launches"], "roofline": roofline,

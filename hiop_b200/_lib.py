@@ -56,6 +56,7 @@ def lib() -> ctypes.CDLL:
     f("hb_ctx_create", c_i, c_i, P(c_vp))
     f("hb_ctx_destroy", c_i, c_vp)
     f("hb_ctx_sync", c_i, c_vp)
+    f("hb_ctx_phase_timeline", c_i, c_vp, c_i, P(ctypes.c_float))
     f("hb_ctx_stream", c_vp, c_vp)
     f("hb_ctx_device", c_i, c_vp)
     f("hb_ctx_enable_timing", c_i, c_vp, c_i)

@@ -45,6 +45,7 @@ extern "C" int hb_ctx_destroy(hb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if(c->oz_state && c->oz_free) c->oz_free(c->oz_state);
+  for(cudaEvent_t e : c->ev_phase) if(e) cudaEventDestroy(e);
   if(c->ws) cudaFree(c->ws);
   if(c->ev_syrk0) { cudaEventDestroy(c->ev_syrk0); cudaEventDestroy(c->ev_syrk1); }
   cudaFree(c->red_dev);
@@ -71,6 +72,30 @@ extern "C" int hb_ctx_last_syrk_ms(hb_ctx* c, float* ms)
   if(!c->timing || !c->syrk_timed) return hb_fail(HB_ERR_STATE, "hb_ctx_last_syrk_ms: no timed SYRK launch recorded%s", "");
   HB_CUDA(cudaEventSynchronize(c->ev_syrk1));
   HB_CUDA(cudaEventElapsedTime(ms, c->ev_syrk0, c->ev_syrk1));
+  return HB_OK;
+}
+
+// Timeline of one quasi-Newton step: with on != 0 the engine records an event after each phase of hb_lowrank_update / condense /
+// solve_compressed; hb_ctx_phase_timeline(ctx, 0, ms) waits for them and returns the phase durations (ms) in the order
+// update, C_aug (slicing + GEMM), all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce), SPD solve, J^T dy, H^-1 rx (second).
+extern "C" int hb_ctx_phase_timeline(hb_ctx* c, int on, float* ms_host10)
+{
+  HB_REQUIRE(c, "null ctx");
+  if(on) {
+    for(int i = 0; i < HB_PH_COUNT; i++)
+      if(!c->ev_phase[i]) HB_CUDA(cudaEventCreate(&c->ev_phase[i]));
+    c->phase_mask = 0;
+    c->phases = true;
+    return HB_OK;
+  }
+  c->phases = false;
+  if(ms_host10) {
+    HB_CUDA(cudaStreamSynchronize(c->stream));
+    for(int i = 1; i < HB_PH_COUNT; i++) {
+      ms_host10[i - 1] = 0.f;
+      if((c->phase_mask >> i & 1u) && (c->phase_mask >> (i - 1) & 1u)) HB_CUDA(cudaEventElapsedTime(&ms_host10[i - 1], c->ev_phase[i - 1], c->ev_phase[i]));
+    }
+  }
   return HB_OK;
 }
 

@@ -69,6 +69,10 @@ struct hb_ctx
   bool timing = false;
   cudaEvent_t ev_syrk0 = nullptr, ev_syrk1 = nullptr;
   bool syrk_timed = false;
+  // phase timeline (hb_ctx_phase_timeline): events recorded at fixed points of one update + condense + solve when enabled
+  bool phases = false;
+  cudaEvent_t ev_phase[16] = {nullptr};
+  unsigned phase_mask = 0;
   // per-context state of the int8-slice condensation (hb_ozaki.cu): slice buffer, exponents, tensor maps, work list
   void* oz_state = nullptr;
   void (*oz_free)(void*) = nullptr;
@@ -80,6 +84,16 @@ struct hb_ctx
 static constexpr int HB_RED_SLOTS = 4096;
 
 int hb_ws_reserve(hb_ctx* ctx, size_t bytes);
+
+// phase marks of the quasi-Newton step (ids are the HB_PH_* below); a no-op unless hb_ctx_phase_timeline switched them on
+enum { HB_PH_START = 0, HB_PH_UPDATE, HB_PH_CAUG, HB_PH_ALLREDUCE, HB_PH_VN, HB_PH_CHOL, HB_PH_HSOLVE1, HB_PH_JX, HB_PH_SPDSOLVE, HB_PH_JTY, HB_PH_HSOLVE2, HB_PH_COUNT };
+inline void hb_phase_mark(hb_ctx* c, int id)
+{
+  if(c->phases && c->ev_phase[id]) {
+    cudaEventRecord(c->ev_phase[id], c->stream);
+    c->phase_mask |= 1u << id;
+  }
+}
 
 // ---- small device helpers ---------------------------------------------------------------------------------
 __device__ __forceinline__ double hb_warp_sum(double v)

@@ -27,9 +27,9 @@ int hb_dense_spd_solve_refine2(hb_ctx* c, int N, const double* F, int ldf, const
 struct hb_big
 {
   cudaStream_t panel_stream = nullptr;
-  cudaEvent_t ev_panel = nullptr, ev_upd = nullptr;
+  cudaEvent_t ev_panel = nullptr, ev_upd = nullptr, ev_upd2 = nullptr;
   double* InvAll = nullptr;         // ceil(N/128) inverses of the 128 x 128 diagonal triangles of the factor (column-major, zeros above)
-  double* W[2] = {nullptr, nullptr}; // LDL^T: W = L*D of the current panel (double-buffered across the look-ahead)
+  double* W[2] = {nullptr, nullptr}; // LDL^T: W = L*D of the current PAIR of panels, 256 p-major rows (double-buffered across the look-ahead)
   double* dinv = nullptr;
   double* partial = nullptr;        // solve: per-CTA partial products
   int* counter = nullptr;           // solve: ticket of the "last CTA finishes the step" pattern (self-resetting)

@@ -701,17 +701,21 @@ k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
   const int tid = threadIdx.x, G = gridDim.x - 1;
   const int nrows = min(SB, N - k0);
   const int r = tid & 127, gsel = tid >> 7; // 8 groups
+  // programmatic dependent launch: the next step's grid may start now (its CTAs prefetch the factor / inverse, which no step writes)
+  // and blocks in griddepcontrol.wait until this grid has completed before it touches x, the partials or the counter
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if(blockIdx.x != 0) {
     // ---- main: partial[b][r] = sum_{j in 64-column chunk b} L(k0 + r, j) x_j ----
     const int b = blockIdx.x - 1;
     const int jb = b * 64;
-    if(tid < 64) S.xs[tid] = (jb + tid < k0) ? x[jb + tid] : 0.0;
     double v[8];
 #pragma unroll
     for(int q = 0; q < 8; q++) {
       const int j = jb + gsel * 8 + q;
       v[q] = (r < nrows && j < k0) ? LC(F, ldf, k0 + r, j) : 0.0;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if(tid < 64) S.xs[tid] = (jb + tid < k0) ? x[jb + tid] : 0.0;
     __syncthreads();
     double acc = 0.0;
 #pragma unroll
@@ -737,6 +741,7 @@ k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
     const int cc = gsel + 8 * q;
     inv[q] = cc <= r ? Inv[cc * BB + r] : 0.0;
   }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
   wait_counter(counter, G);
   gather_partials(S, partial, G, nrows, xk);
@@ -763,18 +768,20 @@ k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x - 1;
   const int nrows = min(SB, N - k0);
   const int k1 = k0 + nrows;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if(blockIdx.x != 0) {
     // ---- main: partial[b][j] = sum_{i in 64-row chunk b below the step} L(i, k0 + j) x_i ----
     const int b = blockIdx.x - 1;
     const int il = tid & 63, cg = tid >> 6; // 64 rows x 16 column groups of 8
     const int i = k1 + b * 64 + il;
-    const double xi = i < N ? x[i] : 0.0;
     double v[8];
 #pragma unroll
     for(int q = 0; q < 8; q++) {
       const int jl = cg * 8 + q;
       v[q] = (i < N && jl < nrows) ? LC(F, ldf, i, k0 + jl) : 0.0;
     }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const double xi = i < N ? x[i] : 0.0;
 #pragma unroll
     for(int q = 0; q < 8; q++) v[q] = hb_warp_sum(v[q] * xi);
     if(lane == 0) {
@@ -801,6 +808,7 @@ k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
       const int cc = warp + 32 * t, rr = lane + 32 * u;
       it[t * 4 + u] = rr >= cc ? Inv[cc * BB + rr] : 0.0;
     }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
   wait_counter(counter, G);
   gather_partials(S, partial, G, nrows, xk);
@@ -865,6 +873,7 @@ int hb_big_init(hb_ctx* c, hb_big* b)
     HB_CUDA(cudaStreamCreateWithPriority(&b->panel_stream, cudaStreamNonBlocking, hi));
     HB_CUDA(cudaEventCreateWithFlags(&b->ev_panel, cudaEventDisableTiming));
     HB_CUDA(cudaEventCreateWithFlags(&b->ev_upd, cudaEventDisableTiming));
+    HB_CUDA(cudaEventCreateWithFlags(&b->ev_upd2, cudaEventDisableTiming));
   }
   return HB_OK;
 }
@@ -876,6 +885,7 @@ void hb_big_release(hb_big* b)
     cudaStreamDestroy(b->panel_stream);
     cudaEventDestroy(b->ev_panel);
     cudaEventDestroy(b->ev_upd);
+    cudaEventDestroy(b->ev_upd2);
     b->panel_stream = nullptr;
   }
   cudaFree(b->InvAll); cudaFree(b->W[0]); cudaFree(b->W[1]); cudaFree(b->dinv); cudaFree(b->partial); cudaFree(b->counter); cudaFree(b->xtmp);
@@ -907,7 +917,7 @@ int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w)
   }
   if(need_w && !b->W[0]) {
     const size_t ldw = (size_t)((N + 7) & ~7);
-    if(cudaMalloc(&b->W[0], sizeof(double) * ldw * BB) != cudaSuccess || cudaMalloc(&b->W[1], sizeof(double) * ldw * BB) != cudaSuccess) {
+    if(cudaMalloc(&b->W[0], sizeof(double) * ldw * 2 * BB) != cudaSuccess || cudaMalloc(&b->W[1], sizeof(double) * ldw * 2 * BB) != cudaSuccess) {
       cudaGetLastError();
       return hb_fail(HB_ERR_ALLOC, "hb_big_reserve: panel scratch allocation failed%s", "");
     }
@@ -917,6 +927,13 @@ int hb_big_reserve(hb_ctx* c, hb_big* b, int N, bool need_w)
 
 // Cholesky (ldl = false) or no-pivot LDL^T (ldl = true) of the column-major-lower triangle; lda must be even and A 16-byte aligned.
 // info_dev: 0 ok, k > 0 = breakdown at column k (1-based). The diagonal-block inverses land in b->InvAll.
+//
+// Schedule: blocks of 128 columns are factored in PAIRS. Inside a pair the first panel updates only the 128 columns of the second
+// (K = 128); the rest of the matrix receives both panels at once (K = 256), which halves the read-modify-write passes over the trailing
+// matrix and the per-tile prologue/epilogue share of the update kernel. Two streams: the panel stream runs
+//   diag(2a) trsm(2a) U1(2a -> block 2a+1) diag(2a+1) trsm(2a+1)
+// while the update stream still applies pair a-1 to the columns beyond; the update stream applies pair a first to the two column
+// blocks the next pair needs (events E_UA, E_UBa release the panel stream one block at a time), then to everything else.
 int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ldl, int* info_dev)
 {
   HB_REQUIRE((lda & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15u) == 0, "hb_big_factor: needs an even leading dimension and a 16-byte aligned matrix");
@@ -924,14 +941,12 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
   const long long ldw = (N + 7) & ~7;
   cudaStream_t su = c->stream, sp = b->panel_stream;
   HB_CUDA(cudaMemsetAsync(info_dev, 0, sizeof(int), su));
-  HB_CUDA(cudaEventRecord(b->ev_upd, su));
+  HB_CUDA(cudaEventRecord(b->ev_upd, su));  // E_UA : the first block of the next pair has received everything
+  HB_CUDA(cudaEventRecord(b->ev_upd2, su)); // E_UBa: so has its second block
   const int nblk = (N + BB - 1) / BB;
-  for(int blk = 0; blk < nblk; blk++) {
+  double* inv16 = b->dinv + BB;
+  auto panel = [&](int blk, double* Wb) -> int { // diagonal block + panel solve of block blk on the panel stream
     const int k0 = blk * BB, nb = N - k0 < BB ? N - k0 : BB, r0 = k0 + nb;
-    double* inv16 = b->dinv + BB;
-    double* Wb = ldl ? b->W[blk & 1] : nullptr;
-    // ---- panel stream: diagonal block, then L21 ----
-    HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd, 0));
     if(ldl) k_diag128<true><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, info_dev, nullptr);
     else k_diag128<false><<<1, DTHREADS, sizeof(DiagSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, info_dev, nullptr);
     HB_LAUNCHED();
@@ -941,27 +956,48 @@ int hb_big_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, bool ld
       else k_trsm_panel<false><<<ntile, 256, sizeof(TrsmSmem), sp>>>(A, lda, N, k0, inv16, b->dinv, nullptr, 0);
       HB_LAUNCHED();
     }
+    return HB_OK;
+  };
+  auto update = [&](cudaStream_t st, const double* P, long long ldp, int kq0, int kb, int r0, int tj0, int ntj) -> int {
+    // A(i,j) -= sum_p P[p][i] * L(j, kq0 + p) on the lower triangle from row/column r0 on, column tiles [tj0, tj0 + ntj) of 64
+    GemmArgs g{};
+    g.P = P; g.ldp = ldp;
+    g.Q = A + (size_t)kq0 * lda; g.ldq = lda; g.qsub = 0;
+    g.kb = kb;
+    g.C = A; g.ldc = lda;
+    g.i_base = r0; g.j_base = r0; g.i_end = N; g.j_end = N; g.tj0 = tj0;
+    const int nti = (N - r0 + TM - 1) / TM;
+    k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj), 256, GemmCfg<64>::SMEM, st>>>(g);
+    HB_LAUNCHED();
+    return HB_OK;
+  };
+  for(int a = 0; 2 * a < nblk; a++) {
+    const int b0 = 2 * a, b1 = 2 * a + 1;
+    const int k0 = b0 * BB;                                   // first column of the pair
+    double* Wp = ldl ? b->W[a & 1] : nullptr;                 // W = L*D of both panels, 256 p-major rows
+    // ---- panel stream ----
+    HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd, 0));
+    HB_CHECK(panel(b0, Wp));
+    if(b1 < nblk) {
+      HB_CUDA(cudaStreamWaitEvent(sp, b->ev_upd2, 0));
+      const int r0 = k0 + BB;
+      const int ntj = (N - r0 + 63) / 64;
+      HB_CHECK(update(sp, ldl ? Wp : A + (size_t)k0 * lda, ldl ? ldw : lda, k0, BB, r0, 0, ntj < 2 ? ntj : 2)); // panel b0 -> columns of block b1
+      HB_CHECK(panel(b1, ldl ? Wp + (size_t)BB * ldw : nullptr));
+    }
     HB_CUDA(cudaEventRecord(b->ev_panel, sp));
     HB_CUDA(cudaStreamWaitEvent(su, b->ev_panel, 0));
+    // ---- update stream: both panels (K = 256) on everything beyond the pair ----
+    const int r0 = k0 + 2 * BB;
     if(r0 < N) {
-      // ---- update stream: next panel's columns first, then the rest ----
-      GemmArgs g{};
-      g.P = ldl ? Wb : A + (size_t)k0 * lda; g.ldp = ldl ? ldw : lda;
-      g.Q = A + (size_t)k0 * lda; g.ldq = lda; g.qsub = 0;
-      g.kb = nb;
-      g.C = A; g.ldc = lda;
-      g.i_base = r0; g.j_base = r0; g.i_end = N; g.j_end = N; g.tj0 = 0;
-      g.W2 = nullptr; g.ldw2 = 0; g.dinv = nullptr; g.state = nullptr;
-      const int nti = (N - r0 + TM - 1) / TM;
       const int ntj = (N - r0 + 63) / 64;
-      k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj < 2 ? ntj : 2), 256, GemmCfg<64>::SMEM, su>>>(g);
-      HB_LAUNCHED();
+      const double* P = ldl ? Wp : A + (size_t)k0 * lda;
+      const long long ldp = ldl ? ldw : lda;
+      HB_CHECK(update(su, P, ldp, k0, 2 * BB, r0, 0, ntj < 2 ? ntj : 2));
       HB_CUDA(cudaEventRecord(b->ev_upd, su));
-      if(ntj > 2) {
-        g.tj0 = 2;
-        k_gemm_pq<64, EPI_SUB><<<dim3(nti, ntj - 2), 256, GemmCfg<64>::SMEM, su>>>(g);
-        HB_LAUNCHED();
-      }
+      if(ntj > 2) HB_CHECK(update(su, P, ldp, k0, 2 * BB, r0, 2, ntj - 2 < 2 ? ntj - 2 : 2));
+      HB_CUDA(cudaEventRecord(b->ev_upd2, su));
+      if(ntj > 4) HB_CHECK(update(su, P, ldp, k0, 2 * BB, r0, 4, ntj - 4));
     }
   }
   // the 128 x 128 inverses of the diagonal triangles (for the solves), all blocks at once
@@ -1034,9 +1070,25 @@ int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, in
     HB_LAUNCHED();
     v = b->xtmp;
   }
+  // every step is launched with programmatic stream serialization: its CTAs start while the previous step still runs, prefetch what
+  // does not depend on it, and wait (griddepcontrol.wait) for its completion before the first dependent access
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(ST);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cfg.attrs = pdl;
+  cfg.numAttrs = 1;
+  const double* InvAll = b->InvAll;
+  double* partial = b->partial;
+  int* counter = b->counter;
   for(int k0 = 0; k0 < N; k0 += SB) {
     const int G = (k0 + 63) / 64;
-    k_solve_fwd_step<<<G + 1, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    cfg.gridDim = dim3(G + 1);
+    cfg.numAttrs = k0 == 0 ? 0 : 1; // the first step follows foreign kernels (factorization, inverses, gather): plain stream order
+    HB_CUDA(cudaLaunchKernelEx(&cfg, k_solve_fwd_step, F, ldf, N, k0, InvAll, v, partial, counter));
     HB_LAUNCHED();
   }
   if(dmode == 1) {
@@ -1050,7 +1102,9 @@ int hb_big_solve(hb_ctx* c, hb_big* b, int N, const double* F, long long ldf, in
     const int nrows = N - k0 < SB ? N - k0 : SB;
     const int below = N - (k0 + nrows);
     const int G = (below + 63) / 64;
-    k_solve_bwd_step<<<G + 1, ST, 0, st>>>(F, ldf, N, k0, b->InvAll, v, b->partial, b->counter);
+    cfg.gridDim = dim3(G + 1);
+    cfg.numAttrs = (k0 == last && dmode != 0) ? 0 : 1; // after the diagonal solve kernel: plain stream order
+    HB_CUDA(cudaLaunchKernelEx(&cfg, k_solve_bwd_step, F, ldf, N, k0, InvAll, v, partial, counter));
     HB_LAUNCHED();
   }
   if(perm_dev) {

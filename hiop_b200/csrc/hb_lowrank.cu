@@ -546,6 +546,7 @@ int condense_finish(hb_lowrank* k)
   hb_ctx* c = k->ctx;
   const int m = k->m, l = k->l, Ma = m + 2 * l;
   HB_CUDA(cudaMemsetAsync(k->info, 0, sizeof(int) * 4, c->stream));
+  hb_phase_mark(c, HB_PH_CAUG);
   if(Ma > 0 && c->nranks > 1) {
     // the symmetric C_aug travels as its packed upper triangle: Ma(Ma+1)/2 doubles instead of Ma^2
     const long long tot = (long long)Ma * (Ma + 1) / 2;
@@ -557,6 +558,7 @@ int condense_finish(hb_lowrank* k)
     k_unpack_upper<<<g, 256, 0, c->stream>>>(Ma, k->Caug, Ma, k->tri);
     HB_LAUNCHED();
   }
+  hb_phase_mark(c, HB_PH_ALLREDUCE);
   if(l > 0) {
     k_build_V<<<(4 * l * l + 127) / 128, 128, 0, c->stream>>>(m, l, k->sigma, k->Caug, Ma, k->SSt, k->Ld, k->Dd_sec, k->V);
     HB_LAUNCHED();
@@ -573,7 +575,9 @@ int condense_finish(hb_lowrank* k)
         m, k->meq, l, k->Caug, Ma, k->U, k->Z, k->Dd_inv, k->Nmat);
     HB_LAUNCHED();
     HB_CHECK(hb_dense_equilibrate(c, m, k->Nmat, m, k->F, m, k->svec));
+    hb_phase_mark(c, HB_PH_VN);
     HB_CHECK(hb_dense_chol_with_inverses(c, m, k->F, m, k->info + 1, k->Finv, &k->have_finv));
+    hb_phase_mark(c, HB_PH_CHOL);
   }
   HB_CUDA(cudaMemcpyAsync(k->info_host, k->info, sizeof(int) * 4, cudaMemcpyDeviceToHost, c->stream));
   return HB_OK;
@@ -721,6 +725,7 @@ extern "C" int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* 
   HB_REQUIRE(k->n == 0 || k->ixl, "hb_lowrank_update: patterns not set");
   hb_ctx* c = k->ctx;
   k->zl = zl; k->sxl = sxl; k->zu = zu; k->sxu = sxu; k->vl = vl; k->sdl = sdl; k->vu = vu; k->sdu = sdu;
+  hb_phase_mark(c, HB_PH_START);
   if(k->n > 0) {
     k_update_x<<<stream_grid(c, k->n), ET, 0, c->stream>>>(k->n, zl, sxl, zu, sxu, k->ixl, k->ixu, k->sigma, k->Dx, k->DhInv);
     HB_LAUNCHED();
@@ -729,6 +734,7 @@ extern "C" int hb_lowrank_update(hb_lowrank* k, const double* zl, const double* 
     k_update_d<<<(k->mineq + 127) / 128, 128, 0, c->stream>>>(k->mineq, vl, sdl, vu, sdu, k->idl, k->idu, k->Dd, k->Dd_inv);
     HB_LAUNCHED();
   }
+  hb_phase_mark(c, HB_PH_UPDATE);
   k->have_update = true;
   k->cond_valid = false;
   return HB_OK;
@@ -779,22 +785,27 @@ extern "C" int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const doub
   const int m = k->m;
   // 1. dx_tmp = (H+Dx)^{-1} rx                                  hiopKKTLinSys.cpp:1146
   HB_CHECK(hess_solve(k, rx, dx));
+  hb_phase_mark(c, HB_PH_HSOLVE1);
   if(m > 0) {
     // 2. rhs = J*dx_tmp - [ryc; ryd]                              :1154-1157
     HB_CHECK(gemv_rows(k, k->J, m, 0.0, k->rhs, 1.0, dx));
+    hb_phase_mark(c, HB_PH_JX);
     k_sub_stacked<<<(m + 127) / 128, 128, 0, c->stream>>>(k->meq, k->mineq, k->rhs, ryc, ryd);
     HB_LAUNCHED();
     // 3. N dy = rhs with residual-driven refinement               :1169, 1192-1350
     HB_CHECK(hb_dense_spd_solve_refine2(c, m, k->F, m, k->have_finv ? k->Finv : nullptr, k->svec, k->Nmat, m, k->rhs, k->dy, k->work, 1e-8, 3,
                                         k->stats));
+    hb_phase_mark(c, HB_PH_SPDSOLVE);
     if(k->meq) HB_CUDA(cudaMemcpyAsync(dyc, k->dy, sizeof(double) * k->meq, cudaMemcpyDeviceToDevice, c->stream));
     if(k->mineq) HB_CUDA(cudaMemcpyAsync(dyd, k->dy + k->meq, sizeof(double) * k->mineq, cudaMemcpyDeviceToDevice, c->stream));
     // 4. rx = rx - J^T dy                                          :1178
     HB_CHECK(gemv_cols(k, k->J, m, 1.0, rx, -1.0, k->dy));
+    hb_phase_mark(c, HB_PH_JTY);
     HB_CUDA(cudaMemcpyAsync(k->stats_host, k->stats, sizeof(double) * 2, cudaMemcpyDeviceToHost, c->stream));
   }
   // 5. dx = (H+Dx)^{-1} rx                                        :1180
   HB_CHECK(hess_solve(k, rx, dx));
+  hb_phase_mark(c, HB_PH_HSOLVE2);
   return HB_OK;
 }
 

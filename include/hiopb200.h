@@ -59,6 +59,11 @@ int hb_ctx_device(hb_ctx* ctx);
  * ran: the FP64 DMMA SYRK (k_syrk_ws) or the int8-slice tcgen05 GEMM (k_oz_gemm) -- on the context stream; hb_ctx_last_syrk_ms waits
  * for it and returns its device duration. */
 int hb_ctx_enable_timing(hb_ctx* ctx, int on);
+/* Per-phase timeline of one quasi-Newton step (per-rank evidence for the multi-GPU runs): hb_ctx_phase_timeline(ctx, 1, NULL) arms the
+ * marks, the next hb_lowrank_update + condense + solve_compressed records an event after each phase, hb_ctx_phase_timeline(ctx, 0, ms)
+ * returns 10 durations in ms: update, C_aug (slicing + GEMM), all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce),
+ * SPD solve, J^T dy, H^-1 rx (second). */
+int hb_ctx_phase_timeline(hb_ctx* ctx, int on, float* ms_host10);
 int hb_ctx_last_syrk_ms(hb_ctx* ctx, float* ms_host);
 
 /* Measured roofline denominators of this device (a few milliseconds each, CUDA events on the context stream):
