@@ -33,7 +33,7 @@ namespace {
 
 constexpr int CS = 16;     // CTAs per cluster
 constexpr int PT = 1024;   // threads per CTA
-constexpr int NBMAX = 32;
+constexpr int NBMAX = 64;  // widest panel (used when the slab of 64 columns fits in the cluster's shared memory)
 #define BK_ALPHA 0.6403882032022076
 
 struct ArgMax
@@ -530,7 +530,8 @@ __global__ void k_bk_advance(int* __restrict__ state)
 // The <= 32 swaps touch <= 64 rows: each thread (one column) reads all affected entries, then writes them to their final places --
 // independent loads, no chain of dependent swaps.
 __global__ void __launch_bounds__(256)
-k_bk_apply_swaps(double* __restrict__ A, long long lda, int N, const int* __restrict__ swaplog_all, int panel_index, int* __restrict__ perm)
+k_bk_apply_swaps(double* __restrict__ A, long long lda, int N, const int* __restrict__ swaplog_all, int panel_index, int* __restrict__ perm,
+                 double* __restrict__ scratch /* 2*NBMAX x ldscr */, long long ldscr)
 {
   __shared__ int rows[2 * NBMAX], src[2 * NBMAX];
   __shared__ int nrow;
@@ -553,12 +554,23 @@ k_bk_apply_swaps(double* __restrict__ A, long long lda, int N, const int* __rest
   const int n = nrow;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if(j < k0) {
-    double v[2 * NBMAX];
+    // all affected entries of column j are staged (reads independent of each other), then written to their final rows
+    for(int q0 = 0; q0 < n; q0 += 8) {
+      double v[8];
 #pragma unroll
-    for(int q = 0; q < 2 * NBMAX; q++) v[q] = q < n ? LC(A, lda, src[q], j) : 0.0;
+      for(int q = 0; q < 8; q++) v[q] = q0 + q < n ? LC(A, lda, src[q0 + q], j) : 0.0;
 #pragma unroll
-    for(int q = 0; q < 2 * NBMAX; q++)
-      if(q < n && src[q] != rows[q]) LC(A, lda, rows[q], j) = v[q];
+      for(int q = 0; q < 8; q++)
+        if(q0 + q < n) scratch[(size_t)(q0 + q) * ldscr + j] = v[q];
+    }
+    for(int q0 = 0; q0 < n; q0 += 8) {
+      double v[8];
+#pragma unroll
+      for(int q = 0; q < 8; q++) v[q] = q0 + q < n ? scratch[(size_t)(q0 + q) * ldscr + j] : 0.0;
+#pragma unroll
+      for(int q = 0; q < 8; q++)
+        if(q0 + q < n && src[q0 + q] != rows[q0 + q]) LC(A, lda, rows[q0 + q], j) = v[q];
+    }
   }
   if(blockIdx.x == 0 && threadIdx.x == 0) {
     int pv[2 * NBMAX];
@@ -623,13 +635,16 @@ long long* g_bkc_prof = nullptr; // diagnostics: device array of 8 cycle counter
 
 } // namespace
 
-// geometry of the cluster panel for a matrix of order N: rows per CTA (S), panel width (NB), dynamic shared memory
-static void bkc_geometry(int N, int* S, int* NB, size_t* smem)
+// geometry of one cluster panel with `rows` active rows: rows per CTA (S), panel width (NB: the widest of 64/32/16/8 whose slab fits),
+// dynamic shared memory
+static void bkc_geometry(int rows, int* S, int* NB, size_t* smem)
 {
-  int s = (N + CS - 1) / CS;
+  int s = (rows + CS - 1) / CS;
   if(s < NBMAX) s = NBMAX;
   s = (s + 31) & ~31;
-  int nb = NBMAX;
+  // 64 columns halve the passes of the trailing update over the matrix but lengthen the in-panel update of every column step:
+  // measured break-even around 3000 active rows (N = 2048 / 4096: 6.4 / 14.0 ms with 32, 6.7 / 14.6 ms with 64; N = 16384: 269 -> 209 ms)
+  int nb = rows >= 3000 ? NBMAX : 32;
   const size_t budget = 200 * 1024;
   while(nb > 8 && ((size_t)nb * s + s) * sizeof(double) + 2 * sizeof(BkStep) > budget) nb >>= 1;
   *S = s; *NB = nb;
@@ -650,11 +665,9 @@ bool hb_bkc_supported(hb_ctx* c, int N)
 int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ipiv_dev, double* dsub_dev, int* perm_dev, double* Wp, long long ldw,
                   int* state_dev /* 4 ints */, int* swaplog_dev, int* info_dev)
 {
+  double* swap_scratch = Wp + (size_t)NBMAX * ldw; // Wp holds NBMAX columns of W followed by 2*NBMAX rows of staging for the interchanges
   HB_REQUIRE((lda & 1) == 0, "hb_bkc_factor: needs an even leading dimension");
   HB_CHECK(hb_big_init(c, b));
-  int S0, NB;
-  size_t smem0;
-  bkc_geometry(N, &S0, &NB, &smem0);
   if(c->device < 16 && !g_bkc_attr[c->device]) {
     HB_CUDA(cudaFuncSetAttribute(k_bk_panel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     HB_CUDA(cudaFuncSetAttribute(k_bk_panel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -666,15 +679,13 @@ int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ip
   HB_CUDA(cudaMemsetAsync(state_dev, 0, sizeof(int) * 4, st));
   k_iota<<<(N + 255) / 256, 256, 0, st>>>(N, perm_dev, dsub_dev);
   HB_LAUNCHED();
-  const int max_panels = (N + (NB - 1) - 1) / (NB - 1) + 1;
-  for(int p = 0; p < max_panels; p++) {
-    const int k0_min = p * (NB - 1);
-    if(k0_min >= N) break;
-    // rows per CTA for this panel (k0 >= k0_min is only known on the device): balanced over the rows that are left
-    int S = (N - k0_min + CS - 1) / CS;
-    if(S < NBMAX) S = NBMAX;
-    S = (S + 31) & ~31;
-    const size_t smem = ((size_t)NB * S + S) * sizeof(double) + 2 * sizeof(BkStep);
+  // The origin k0 of a panel is only known on the device (a panel factors NB or NB-1 columns); the host tracks its bounds
+  // k0_min <= k0 <= k0_max to size the launches: rows per CTA and panel width from the rows that are certainly left at most.
+  int k0_min = 0, k0_max = 0;
+  for(int p = 0; k0_min < N; p++) {
+    int S, NB;
+    size_t smem;
+    bkc_geometry(N - k0_min, &S, &NB, &smem);
     int threads = S < PT ? S : PT; // one row per thread where possible: fewer idle warps in every barrier / shuffle stage
     if(threads < 128) threads = 128;
     if(g_bkc_prof) k_bk_panel<true><<<CS, threads, smem, st>>>(A, lda, N, Wp, ldw, NB, S, ipiv_dev, dsub_dev, state_dev, swaplog_dev, p, g_bkc_prof);
@@ -683,17 +694,17 @@ int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ip
     // the interchanges on the previous columns and on the permutation run beside the trailing update (disjoint data)
     HB_CUDA(cudaEventRecord(b->ev_upd, st));
     HB_CUDA(cudaStreamWaitEvent(side, b->ev_upd, 0));
-    if(k0_min > 0) {
-      const int kmax = p * NB < N ? p * NB : N;
-      k_bk_apply_swaps<<<(kmax + 255) / 256, 256, 0, side>>>(A, lda, N, swaplog_dev, p, perm_dev);
-    } else {
-      k_bk_apply_swaps<<<1, 256, 0, side>>>(A, lda, N, swaplog_dev, p, perm_dev);
+    {
+      const int kmax = k0_max < N ? k0_max : N;
+      k_bk_apply_swaps<<<kmax > 0 ? (kmax + 255) / 256 : 1, 256, 0, side>>>(A, lda, N, swaplog_dev, p, perm_dev, swap_scratch, ldw);
+      HB_LAUNCHED();
     }
-    HB_LAUNCHED();
     const int r0_min = k0_min + (NB - 1);
     if(r0_min < N) HB_CHECK(hb_big_trailing_from_state(c, N, A, lda, Wp, ldw, state_dev, r0_min, st));
     k_bk_advance<<<1, 32, 0, st>>>(state_dev);
     HB_LAUNCHED();
+    k0_min += NB - 1;
+    k0_max += NB;
   }
   HB_CUDA(cudaEventRecord(b->ev_panel, side));
   HB_CUDA(cudaStreamWaitEvent(st, b->ev_panel, 0));

@@ -53,4 +53,5 @@ int hb_bkc_factor(hb_ctx* c, hb_big* b, int N, double* A, long long lda, int* ip
 int hb_bkc_inertia(hb_ctx* c, int N, const double* F, long long ldf, const int* ipiv_dev, const double* dsub_dev, int* out3_dev);
 int hb_bkc_dsolve(hb_ctx* c, int N, const double* F, long long ldf, const int* ipiv_dev, const double* dsub_dev, double* x);
 int hb_bkc_profile(hb_ctx* c, int on, long long* prof_host8);
-#define HB_BKC_SWAPLOG_INTS(N) ((size_t)((N) / 7 + 4) * 68)
+#define HB_BKC_SWAPLOG_INTS(N) ((size_t)((N) / 7 + 4) * 132)
+#define HB_BKC_W_DOUBLES(ldw) ((size_t)(ldw) * (64 + 128)) /* W = L*D of a panel (<= 64 columns) + staging rows of the interchange kernel */

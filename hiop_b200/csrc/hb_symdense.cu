@@ -117,7 +117,7 @@ extern "C" int hb_symdense_matrix_changed(hb_symdense* s, int mode)
       if(!s->dsub) {
         if(cudaMalloc(&s->dsub, sizeof(double) * (N + 2)) != cudaSuccess || cudaMalloc(&s->perm, sizeof(int) * (N + 2)) != cudaSuccess ||
            cudaMalloc(&s->bk_state, sizeof(int) * 4) != cudaSuccess || cudaMalloc(&s->swaplog, sizeof(int) * HB_BKC_SWAPLOG_INTS(N)) != cudaSuccess ||
-           cudaMalloc(&s->Wp, sizeof(double) * (size_t)ldw * 32) != cudaSuccess) {
+           cudaMalloc(&s->Wp, sizeof(double) * HB_BKC_W_DOUBLES(ldw)) != cudaSuccess) {
           cudaGetLastError();
           return hb_fail(HB_ERR_ALLOC, "hb_symdense_matrix_changed: cannot allocate the Bunch-Kaufman scratch%s", "");
         }
