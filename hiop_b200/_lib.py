@@ -102,6 +102,14 @@ def lib() -> ctypes.CDLL:
     f("hb_mat_times_vec", c_i, c_vp, c_i, c_ll, c_dp, c_ll, c_d, c_dp, c_d, c_dp)
     f("hb_mat_trans_times_vec", c_i, c_vp, c_i, c_ll, c_dp, c_ll, c_d, c_dp, c_d, c_dp)
     # symdense
+    f("hb_mat_times_mat_trans", c_i, c_vp, c_i, c_i, c_ll, c_dp, c_ll, c_dp, c_ll, c_d, c_dp, c_ll, c_d)
+    f("hb_mat_add_sub_diagonal", c_i, c_vp, c_dp, c_ll, c_i, c_i, c_d, c_dp, c_i)
+    f("hb_mat_add_matrix", c_i, c_vp, c_i, c_i, c_dp, c_ll, c_d, c_dp, c_ll)
+    f("hb_mat_copy_rows_from", c_i, c_vp, c_i, c_i, c_dp, c_ll, c_dp, c_ll, c_vp)
+    f("hb_mat_copy_block", c_i, c_vp, c_i, c_i, c_dp, c_ll, c_i, c_i, c_dp, c_ll, c_i, c_i)
+    f("hb_mat_trans_add_to_sym_upper", c_i, c_vp, c_i, c_i, c_dp, c_ll, c_i, c_i, c_d, c_dp, c_ll)
+    f("hb_mat_add_upper_to_sym_upper", c_i, c_vp, c_i, c_dp, c_ll, c_i, c_d, c_dp, c_ll)
+    f("hb_lowrank_test_direction", c_i, c_vp, c_dp, c_dp, c_dp, c_dp, c_d, P(c_d))
     f("hb_symdense_create", c_i, c_vp, c_i, P(c_vp))
     f("hb_symdense_destroy", c_i, c_vp)
     f("hb_symdense_matrix", c_vp, c_vp)

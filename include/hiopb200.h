@@ -135,6 +135,24 @@ int hb_mat_times_vec(hb_ctx*, int m, long long n, const double* A, long long lda
 int hb_mat_trans_times_vec(hb_ctx*, int m, long long n, const double* A, long long lda, double beta, double* y,
                            double alpha, const double* x);
 
+/* hiopMatrixDenseRowMajor primitives as standalone calls (row-major, leading dimensions in elements):
+ *   hb_mat_times_mat_trans           C (m x k) = beta C + alpha A (m x n) B (k x n)^T          timesMatTrans_local  :646-674 (local product)
+ *   hb_mat_add_sub_diagonal          M[s+i][s+i] += alpha * d[src+i] (d == NULL: += alpha)     addDiagonal / addSubDiagonal :703-764
+ *   hb_mat_add_matrix                Y += alpha X                                             addMatrix :766-776
+ *   hb_mat_copy_rows_from            dst row i = src row rows_idx[i] (device int indices)      copyRowsFrom :169-197
+ *   hb_mat_copy_block                dst block at (dst_i,dst_j) = src block at (src_i,src_j)   copyBlockFromMatrix / copyFromMatrixBlock :200-236
+ *   hb_mat_trans_add_to_sym_upper    W(row_start+j, col_start+i) += alpha A(i,j)               transAddToSymDenseMatrixUpperTriangle :779-798
+ *   hb_mat_add_upper_to_sym_upper    W diag block += alpha triu(A)                             addUpperTriangleToSymDenseMatrixUpperTriangle :810-829 */
+int hb_mat_times_mat_trans(hb_ctx*, int m, int k, long long n, const double* A, long long lda, const double* B, long long ldb, double beta, double* C,
+                           long long ldc, double alpha);
+int hb_mat_add_sub_diagonal(hb_ctx*, double* M, long long ld, int start_on_dest_diag, int num_elems, double alpha, const double* d_or_null,
+                            int start_on_src_vec);
+int hb_mat_add_matrix(hb_ctx*, int m, int n, double* Y, long long ldy, double alpha, const double* X, long long ldx);
+int hb_mat_copy_rows_from(hb_ctx*, int n_rows, int n_cols, double* dst, long long ldd, const double* src, long long lds, const int* rows_idx_dev);
+int hb_mat_copy_block(hb_ctx*, int m, int n, double* dst, long long ldd, int dst_i, int dst_j, const double* src, long long lds, int src_i, int src_j);
+int hb_mat_trans_add_to_sym_upper(hb_ctx*, int m, int n, const double* A, long long lda, int row_start, int col_start, double alpha, double* W, long long ldw);
+int hb_mat_add_upper_to_sym_upper(hb_ctx*, int n, const double* A, long long lda, int diag_start, double alpha, double* W, long long ldw);
+
 /* ------------------------------------------------------------------------------------------------------------
  * hiopLinSolverSymDense (B1; src/LinAlg/hiopLinSolver.hpp:78-128, LAPACK twin hiopLinSolverSymDenseLapack.hpp:75-192,
  * MAGMA twins hiopLinSolverSymDenseMagma.cpp:120-270, 324-476)
@@ -296,6 +314,11 @@ int hb_lowrank_compute_directions_w_ir(hb_lowrank* k, const double* const* res, 
 /* y = K x with the full (unsymmetric) 12 x 12 block KKT operator hiopMatVecKKTFullOpr::times_vec
  * (hiopKKTLinSys.cpp:1619-1733); x, y: HOST arrays of 12 DEVICE pointers in the order of dir / res above. */
 int hb_lowrank_kkt_full_times_vec(hb_lowrank* k, const double* const* x, double* const* y);
+/* hiopKKTLinSysCompressed::test_direction (hiopKKTLinSys.cpp:455-509) for the low-rank Hessian: dWd = dx^T (B_k + D_x + delta_wx) dx +
+ * dd^T (D_d + delta_wd) dd against neg_curv_test_fact (||dx||^2 + ||dd||^2). delta_* may be NULL (the quasi-Newton driver runs with
+ * hiopPDPerturbationNull). out_host2 = {dWd, ||dx||^2 + ||dd||^2}. Returns 1 (accept), 0 (negative curvature), < 0 on error. */
+int hb_lowrank_test_direction(hb_lowrank* k, const double* dx, const double* dd, const double* delta_wx, const double* delta_wd, double neg_curv_test_fact,
+                              double* out_host2);
 /* x = (B_k + D_x)^{-1} rhs  (hiopHessianLowRank::solve :495-540) */
 int hb_lowrank_hess_solve(hb_lowrank* k, const double* rhs, double* x);
 /* y = beta*y + alpha*(B_k [+ D_x]) x in the compact form (same operator as the recursive timesVecCmn :974-1059) */
