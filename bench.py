@@ -521,7 +521,8 @@ def run_engine(args):
 
         # ---- end to end through the host-buffer entry point (public API a HiOp adapter calls when mem_space is host) ----
         e2e = None
-        if world == 1 and not args.no_e2e:
+        # N>1: every rank uploads its own column shard from pinned host memory (bounded to 4 GB of pinned J per rank)
+        if not args.no_e2e and (world == 1 or 8.0 * m * n_local <= 4.0e9):
             host = {}
             for key in ("zl", "sxl", "zu", "sxu", "vl", "sdl", "vu", "sdu", "rx", "ryc", "ryd"):
                 host[key] = torch.empty(T[key].shape, dtype=torch.float64, pin_memory=True)
@@ -539,19 +540,29 @@ def run_engine(args):
                 k.kkt_system_host(Jn[:m_eq], Jn[m_eq:], it, host["rx"].numpy(), host["ryc"].numpy(), host["ryd"].numpy(),
                                   hdx.numpy(), hyc.numpy(), hyd.numpy())
             e2e_steps = max(2, min(args.steps, 5))
-            h2d = 8 * (m * n_local + 5 * n_local + 4 * m_ineq + m)
+            h2d = 8 * (m * n_local + 5 * n_local + 4 * m_ineq + m)   # this rank's bytes; the line reports the sum over ranks
             d2h = 8 * (n_local + m)
+            if world > 1:
+                t = torch.tensor([h2d, d2h], dtype=torch.float64, device=ctx.device)
+                dist.all_reduce(t)
+                h2d, d2h = int(t[0].item()), int(t[1].item())
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             res = {}
             for name in ("auto", "oz8"):
                 set_mode(name)
                 e2e_step()
+                barrier()
                 e0.record()
                 for _ in range(e2e_steps):
                     e2e_step()
                 e1.record()
-                torch.cuda.synchronize()
-                res[name] = (e0.elapsed_time(e1) / e2e_steps, k.condense_mode_used())
+                barrier()
+                ms_e = e0.elapsed_time(e1) / e2e_steps
+                if world > 1:
+                    t = torch.tensor([ms_e], dtype=torch.float64, device=ctx.device)
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                    ms_e = float(t.item())
+                res[name] = (ms_e, k.condense_mode_used())
             set_mode(args.condense)
             best = min(res, key=lambda q: res[q][0])
             e2e = {"value": 1e3 / res[best][0], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": res[best][0],
@@ -843,9 +854,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
-    ap.add_argument("--n", type=int, default=N_FULL)
-    ap.add_argument("--m", type=int, default=M_FULL)
-    ap.add_argument("--l", type=int, default=L_MEM)
+    # --kkt-n/--kkt-m/--kkt-l: under `python -m torch.distributed.run`, argparse rejects "--n"/"--m" as ambiguous launcher
+    # abbreviations before it reaches the script's own arguments, so the long spellings are the ones to use there
+    ap.add_argument("--n", "--kkt-n", dest="n", type=int, default=int(os.environ.get("HB_BENCH_N", N_FULL)))
+    ap.add_argument("--m", "--kkt-m", dest="m", type=int, default=int(os.environ.get("HB_BENCH_M", M_FULL)))
+    ap.add_argument("--l", "--kkt-l", dest="l", type=int, default=int(os.environ.get("HB_BENCH_L", L_MEM)))
     ap.add_argument("--condense", default="auto", choices=["auto", "dmma", "oz6", "oz7", "oz8"],
                     help="GEMM part of the condensation: auto (library default), exact FP64 DMMA, or INT8-slice tcgen05 with 6/7/8 slices")
     ap.add_argument("--no-e2e", action="store_true")

@@ -222,7 +222,8 @@ k_gemv_rows_partial(int m, long long n, const double* __restrict__ A, long long 
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) && ((k0 & 1) == 0);
-  for(int i = warp; i < m; i += GR_THREADS / 32) {
+  // blockIdx.y interleaves the rows among gridDim.y CTAs of the same column chunk (short local column ranges)
+  for(int i = warp + (GR_THREADS / 32) * blockIdx.y; i < m; i += (GR_THREADS / 32) * gridDim.y) {
     const double* row = A + (size_t)i * lda + k0;
     double acc = 0.0;
     if(vec) {
@@ -262,15 +263,21 @@ k_gemv_rows_final(int m, int nchunks, const double* __restrict__ partial, double
   }
 }
 
-// y[k] = beta*y[k] + alpha*sum_i A[i][k]*x[i]; each thread owns two adjacent columns
+// y[k] = beta*y[k] + alpha*sum_i A[i][k]*x[i]; each thread owns two adjacent columns. With RG > 1 the CTA covers ET/RG column
+// pairs and its RG thread groups take interleaved rows (combined in a fixed order through shared memory): short local column
+// ranges (a rank's shard of n) still fill the machine.
 constexpr int GC_ROWS = 1024; // rows of x staged per pass
+template <int RG>
 __global__ void __launch_bounds__(ET)
 k_gemv_cols(int m, long long n, const double* __restrict__ A, long long lda, const double* __restrict__ x, double beta,
             double* __restrict__ y, double alpha)
 {
+  constexpr int CP = ET / RG; // column pairs per CTA
   __shared__ double sx[GC_ROWS];
+  __shared__ double2 red[RG > 1 ? ET : 1];
   const bool vec = ((lda & 1) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0);
-  const long long k = ((long long)blockIdx.x * ET + threadIdx.x) * 2;
+  const int cp = threadIdx.x % CP, rg = threadIdx.x / CP;
+  const long long k = ((long long)blockIdx.x * CP + cp) * 2;
   double a0 = 0.0, a1 = 0.0;
   for(int i0 = 0; i0 < m; i0 += GC_ROWS) {
     const int nr = min(GC_ROWS, m - i0);
@@ -281,18 +288,29 @@ k_gemv_cols(int m, long long n, const double* __restrict__ A, long long lda, con
       const double* col = A + (size_t)i0 * lda + k;
       if(vec && k + 1 < n) {
 #pragma unroll 8
-        for(int i = 0; i < nr; i++) {
+        for(int i = rg; i < nr; i += RG) {
           const double2 v = *reinterpret_cast<const double2*>(col + (size_t)i * lda);
           a0 += v.x * sx[i];
           a1 += v.y * sx[i];
         }
       } else {
 #pragma unroll 4
-        for(int i = 0; i < nr; i++) {
+        for(int i = rg; i < nr; i += RG) {
           a0 += col[(size_t)i * lda] * sx[i];
           if(k + 1 < n) a1 += col[(size_t)i * lda + 1] * sx[i];
         }
       }
+    }
+  }
+  if(RG > 1) {
+    red[threadIdx.x] = make_double2(a0, a1);
+    __syncthreads();
+    if(rg != 0) return;
+    a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for(int g = 0; g < RG; g++) {
+      a0 += red[g * CP + cp].x;
+      a1 += red[g * CP + cp].y;
     }
   }
   if(k < n) {
@@ -415,7 +433,9 @@ int gemv_rows(hb_lowrank* k, const double* A, int m, double beta, double* y, dou
   const int nchunks = (int)((k->n + GR_CHUNK - 1) / GR_CHUNK);
   HB_CHECK(hb_ws_reserve(c, sizeof(double) * (size_t)(nchunks > 0 ? nchunks : 1) * m));
   if(nchunks > 0) {
-    k_gemv_rows_partial<<<nchunks, GR_THREADS, 0, c->stream>>>(m, k->n, A, k->n, x, (double*)c->ws);
+    int rsplit = (4 * c->num_sms + nchunks - 1) / nchunks; // at least ~4 CTAs per SM in flight
+    rsplit = rsplit < 1 ? 1 : (rsplit > 8 ? 8 : rsplit);
+    k_gemv_rows_partial<<<dim3(nchunks, rsplit), GR_THREADS, 0, c->stream>>>(m, k->n, A, k->n, x, (double*)c->ws);
     HB_LAUNCHED();
   }
   if(c->nranks > 1) {
@@ -435,7 +455,10 @@ int gemv_cols(hb_lowrank* k, const double* A, int m, double beta, double* y, dou
   hb_ctx* c = k->ctx;
   if(k->n == 0) return HB_OK;
   const long long pairs = (k->n + 1) / 2;
-  k_gemv_cols<<<(unsigned)((pairs + ET - 1) / ET), ET, 0, c->stream>>>(m, k->n, A, k->n, x, beta, y, alpha);
+  const long long ctas1 = (pairs + ET - 1) / ET;
+  if(ctas1 >= 8LL * c->num_sms || m < 64) k_gemv_cols<1><<<(unsigned)ctas1, ET, 0, c->stream>>>(m, k->n, A, k->n, x, beta, y, alpha);
+  else if(ctas1 >= 2LL * c->num_sms) k_gemv_cols<4><<<(unsigned)((pairs + ET / 4 - 1) / (ET / 4)), ET, 0, c->stream>>>(m, k->n, A, k->n, x, beta, y, alpha);
+  else k_gemv_cols<8><<<(unsigned)((pairs + ET / 8 - 1) / (ET / 8)), ET, 0, c->stream>>>(m, k->n, A, k->n, x, beta, y, alpha);
   HB_LAUNCHED();
   return HB_OK;
 }
@@ -1008,7 +1031,7 @@ extern "C" int hb_mat_trans_times_vec(hb_ctx* c, int m, long long n, const doubl
   HB_REQUIRE(c && m >= 0 && n >= 0 && lda >= n, "hb_mat_trans_times_vec: bad arguments");
   if(n == 0) return HB_OK;
   const long long pairs = (n + 1) / 2;
-  k_gemv_cols<<<(unsigned)((pairs + ET - 1) / ET), ET, 0, c->stream>>>(m, n, A, lda, x, beta, y, alpha);
+  k_gemv_cols<1><<<(unsigned)((pairs + ET - 1) / ET), ET, 0, c->stream>>>(m, n, A, lda, x, beta, y, alpha);
   HB_LAUNCHED();
   return HB_OK;
 }

@@ -40,8 +40,10 @@ k_times_mat_trans(int m, int kk, long long n, const double* __restrict__ A, long
 // M[dst0+i][dst0+i] += alpha * (d ? d[src0+i] : 1)
 __global__ void k_add_sub_diag(double* __restrict__ M, long long ld, int dst0, int num, double alpha, const double* __restrict__ d, int src0)
 {
-  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num; i += gridDim.x * blockDim.x)
-    M[(size_t)(dst0 + i) * ld + dst0 + i] += d ? alpha * d[src0 + i] : alpha;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < num; i += gridDim.x * blockDim.x) {
+    double* q = &M[(size_t)(dst0 + i) * ld + dst0 + i];
+    *q = __dadd_rn(*q, d ? __dmul_rn(alpha, d[src0 + i]) : alpha); // product rounded before the add, like the host loops
+  }
 }
 // Y(i,j) += alpha X(i,j)
 __global__ void k_add_matrix(int m, int n, double* __restrict__ Y, long long ldy, double alpha, const double* __restrict__ X, long long ldx)
@@ -49,7 +51,7 @@ __global__ void k_add_matrix(int m, int n, double* __restrict__ Y, long long ldy
   const long long tot = (long long)m * n;
   for(long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / n), j = (int)(e % n);
-    Y[(size_t)i * ldy + j] += alpha * X[(size_t)i * ldx + j];
+    Y[(size_t)i * ldy + j] = __dadd_rn(Y[(size_t)i * ldy + j], __dmul_rn(alpha, X[(size_t)i * ldx + j]));
   }
 }
 // dst(i, j) = src(rows ? rows[i] : i + i0, j0 + j) for an m x n block
@@ -70,7 +72,8 @@ __global__ void k_trans_add_upper(int m, int n, const double* __restrict__ A, lo
   const long long tot = (long long)m * n;
   for(long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(e / m), i = (int)(e % m); // i fastest: contiguous writes along W's row (row_start + j)
-    W[(size_t)(row_start + j) * ldw + col_start + i] += alpha * A[(size_t)i * lda + j];
+    double* q = &W[(size_t)(row_start + j) * ldw + col_start + i];
+    *q = __dadd_rn(*q, __dmul_rn(alpha, A[(size_t)i * lda + j]));
   }
 }
 // W(diag_start + i, diag_start + j) += alpha A(i,j) for j >= i
@@ -79,7 +82,10 @@ __global__ void k_add_upper_to_upper(int n, const double* __restrict__ A, long l
   const long long tot = (long long)n * n;
   for(long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / n), j = (int)(e % n);
-    if(j >= i) W[(size_t)(diag_start + i) * ldw + diag_start + j] += alpha * A[(size_t)i * lda + j];
+    if(j >= i) {
+      double* q = &W[(size_t)(diag_start + i) * ldw + diag_start + j];
+      *q = __dadd_rn(*q, __dmul_rn(alpha, A[(size_t)i * lda + j]));
+    }
   }
 }
 // partial[blk] = {sum (w[i] + dw[i]) x[i]^2, sum x[i]^2}

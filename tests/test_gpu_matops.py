@@ -144,8 +144,7 @@ def test_lowrank_test_direction(ctx):
     dx, dd = r.standard_normal(P.n), r.standard_normal(P.m_ineq)
     dwx, dwd = np.full(P.n, 1e-3), np.full(P.m_ineq, 2e-3)
     Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P.zl, P.sxl, P.zu, P.sxu, P.ixl, P.ixu, P.vl, P.sdl, P.vu, P.sdu, P.idl, P.idu, P.sigma)
-    Bdx = np.zeros(P.n)
-    ko.hess_times_vec(P.St, P.Yt, P.sigma, Dx, 0.0, Bdx, 1.0, dx, False)
+    Bdx = ko.hess_times_vec(P.St, P.Yt, P.sigma, Dx, 0.0, np.zeros(P.n), 1.0, dx, False)
     dWd = Bdx @ dx + ((Dx + dwx) * dx) @ dx + ((Dd + dwd) * dd) @ dd
     xs = dx @ dx + dd @ dd
     out = (ctypes.c_double * 2)()
