@@ -7,7 +7,8 @@
 #include <cstdlib>
 
 int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool aligned16, const double* d, double* C, int ldc);
-int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool rows_aligned16, const double* d, double* C, int ldc, int S);
+int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool rows_aligned16, const double* d, double* C, int ldc, int S,
+                       const double* dot_x, double* dot_out);
 
 namespace {
 
@@ -375,6 +376,18 @@ __global__ void k_sub_stacked(int meq, int mineq, double* __restrict__ rhs, cons
   for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) rhs[i] -= (i < meq ? ryc[i] : ryd[i - meq]);
 }
 
+// rhs[i] = tdot[i] - sum_q Z[i][q] p[q] - ry[i],  p = [sigma*tdot[m..m+l); tdot[m+l..m+2l)]   (fused steps 1-2 of solveCompressed)
+__global__ void k_fused_rhs(int m, int meq, int l, double sigma, const double* __restrict__ tdot, const double* __restrict__ Z,
+                            const double* __restrict__ ryc, const double* __restrict__ ryd, double* __restrict__ rhs)
+{
+  const int n2 = 2 * l;
+  for(int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+    double corr = 0.0;
+    for(int q = 0; q < n2; q++) corr += Z[(size_t)i * n2 + q] * (q < l ? sigma * tdot[m + q] : tdot[m + q]);
+    rhs[i] = (tdot[i] - corr) - (i < meq ? ryc[i] : ryd[i - meq]);
+  }
+}
+
 } // namespace
 
 // =============================================================================================================
@@ -478,7 +491,7 @@ int hess_solve(hb_lowrank* k, const double* rhs, double* x)
   return HB_OK;
 }
 
-int condense_enqueue(hb_lowrank* k, int mode);
+int condense_enqueue(hb_lowrank* k, int mode, const double* fuse_rx = nullptr);
 int condense_finish(hb_lowrank* k);
 
 int resolve_global_n(hb_lowrank* k)
@@ -497,7 +510,7 @@ int resolve_global_n(hb_lowrank* k)
 
 // Enqueues the whole condensation (C_aug, all-reduce, V, N, equilibrated Cholesky) without touching the host. The info words are
 // copied to pinned memory; condense_check() looks at them after a stream synchronisation.
-int do_condense_async(hb_lowrank* k)
+int do_condense_async(hb_lowrank* k, const double* fuse_rx = nullptr)
 {
   HB_REQUIRE(k->have_update, "hb_lowrank_condense: call hb_lowrank_update first");
   HB_REQUIRE(k->J || k->m == 0, "hb_lowrank_condense: Jacobian not set");
@@ -510,7 +523,7 @@ int do_condense_async(hb_lowrank* k)
     HB_CHECK(resolve_global_n(k));
     mode = (k->n_global >= 32768 && Ma >= 64) ? 8 : 0;
   }
-  HB_CHECK(condense_enqueue(k, mode));
+  HB_CHECK(condense_enqueue(k, mode, fuse_rx));
   k->check_pending = true;
   k->cond_valid = true; // optimistic: a failure is reported by the next synchronous call (hb_lowrank_check / hb_lowrank_condense)
   return HB_OK;
@@ -551,14 +564,23 @@ int do_condense(hb_lowrank* k)
   return rc;
 }
 
-int condense_enqueue(hb_lowrank* k, int mode)
+// fuse_rx (optional): the x-block of the right-hand side the caller is about to solve for. The int8-slice condensation has to sweep all
+// rows for their maxima anyway; the same sweep then leaves tdot = [J; S; Y] (DhInv .* rx), from which step 2 of solveCompressed follows
+// without reading J again (see solve_compressed).
+int condense_enqueue(hb_lowrank* k, int mode, const double* fuse_rx)
 {
   hb_ctx* c = k->ctx;
   const int m = k->m, l = k->l, Ma = m + 2 * l;
+  k->tdot_valid = false;
   if(Ma > 0) {
     k->condense_used = mode;
     if(mode == 0) HB_CHECK(hb_syrk_rows(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma));
-    else HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, mode));
+    else {
+      const bool fuse = fuse_rx && m > 0;
+      if(fuse && k->n == 0) HB_CUDA(cudaMemsetAsync(k->tdot, 0, sizeof(double) * Ma, c->stream));
+      HB_CHECK(hb_syrk_rows_ozaki(c, Ma, k->n, k->rowptr_dev, k->rows_aligned, k->DhInv, k->Caug, Ma, mode, fuse ? fuse_rx : nullptr, fuse ? k->tdot : nullptr));
+      k->tdot_valid = fuse;
+    }
   }
   return condense_finish(k);
 }
@@ -573,13 +595,16 @@ int condense_finish(hb_lowrank* k)
   if(Ma > 0 && c->nranks > 1) {
     // the symmetric C_aug travels as its packed upper triangle: Ma(Ma+1)/2 doubles instead of Ma^2
     const long long tot = (long long)Ma * (Ma + 1) / 2;
-    if(!k->tri) HB_CHECK(dmalloc(&k->tri, (size_t)(k->m + 2 * k->lmax) * (k->m + 2 * k->lmax + 1) / 2));
+    if(!k->tri) HB_CHECK(dmalloc(&k->tri, (size_t)(k->m + 2 * k->lmax) * (k->m + 2 * k->lmax + 1) / 2 + (size_t)(k->m + 2 * k->lmax)));
     const int g = (int)((tot + 255) / 256 < (long long)c->num_sms * 8 ? (tot + 255) / 256 : (long long)c->num_sms * 8);
     k_pack_upper<<<g, 256, 0, c->stream>>>(Ma, k->Caug, Ma, k->tri);
     HB_LAUNCHED();
-    HB_CHECK(hb_allreduce_sum(c, k->tri, tot));
+    // the fused row dots ride behind the triangle in the same reduction
+    if(k->tdot_valid) HB_CUDA(cudaMemcpyAsync(k->tri + tot, k->tdot, sizeof(double) * Ma, cudaMemcpyDeviceToDevice, c->stream));
+    HB_CHECK(hb_allreduce_sum(c, k->tri, tot + (k->tdot_valid ? Ma : 0)));
     k_unpack_upper<<<g, 256, 0, c->stream>>>(Ma, k->Caug, Ma, k->tri);
     HB_LAUNCHED();
+    if(k->tdot_valid) HB_CUDA(cudaMemcpyAsync(k->tdot, k->tri + tot, sizeof(double) * Ma, cudaMemcpyDeviceToDevice, c->stream));
   }
   hb_phase_mark(c, HB_PH_ALLREDUCE);
   if(l > 0) {
@@ -647,6 +672,7 @@ extern "C" int hb_lowrank_create(hb_ctx* c, long long n_local, int m_eq, int m_i
   HB_CHECK(dmalloc(&k->Finv, HB_CHOL_INV_DOUBLES(m > 0 ? m : 1)));
   HB_CHECK(dmalloc(&k->stats, 4));
   HB_CHECK(dmalloc(&k->nv1, n_local)); HB_CHECK(dmalloc(&k->nv2, n_local));
+  HB_CHECK(dmalloc(&k->tdot, (size_t)Mamax));
   HB_CHECK(dmalloc(&k->p2l, l2));
   k->md_grid = stream_grid(c, n_local);
   HB_CHECK(dmalloc(&k->md_partial, (size_t)k->md_grid * (l2 > 0 ? l2 : 1)));
@@ -667,7 +693,7 @@ extern "C" int hb_lowrank_destroy(hb_lowrank* k)
   cudaSetDevice(k->ctx->device);
   cudaStreamSynchronize(k->ctx->stream);
   double* bufs[] = {k->Dx, k->DhInv, k->Dd, k->Dd_inv, k->Jpack, k->Caug, k->SSt, k->Ld, k->Dd_sec, k->V, k->Mdir, k->U, k->Z, k->Nmat, k->F,
-                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv, k->Ctmp, k->tri};
+                    k->svec, k->rhs, k->dy, k->work, k->stats, k->nv1, k->nv2, k->p2l, k->md_partial, k->mi1, k->mi2, k->mi3, k->hJ, k->kry, k->kry_m, k->sec_S, k->sec_Y, k->sec_xprev, k->sec_gprev, k->sec_Jprev, k->lsq_M, k->Finv, k->Ctmp, k->tri, k->tdot};
   for(double* b : bufs) if(b) cudaFree(b);
   for(double* b : k->hbuf) if(b) cudaFree(b);
   cudaFree(k->ipivV); cudaFree(k->ipivM); cudaFree(k->info); cudaFree(k->rowptr_dev);
@@ -804,17 +830,35 @@ extern "C" int hb_lowrank_solve_compressed(hb_lowrank* k, double* rx, const doub
   HB_REQUIRE(k->n == 0 || (rx && dx), "hb_lowrank_solve_compressed: null x block");
   HB_REQUIRE((k->meq == 0 || (ryc && dyc)) && (k->mineq == 0 || (ryd && dyd)), "hb_lowrank_solve_compressed: null dual block");
   hb_ctx* c = k->ctx;
-  if(!k->cond_valid) HB_CHECK(do_condense_async(k)); // breakdowns surface at the next synchronous call (hb_lowrank_check)
   const int m = k->m;
-  // 1. dx_tmp = (H+Dx)^{-1} rx                                  hiopKKTLinSys.cpp:1146
-  HB_CHECK(hess_solve(k, rx, dx));
-  hb_phase_mark(c, HB_PH_HSOLVE1);
-  if(m > 0) {
-    // 2. rhs = J*dx_tmp - [ryc; ryd]                              :1154-1157
-    HB_CHECK(gemv_rows(k, k->J, m, 0.0, k->rhs, 1.0, dx));
-    hb_phase_mark(c, HB_PH_JX);
-    k_sub_stacked<<<(m + 127) / 128, 128, 0, c->stream>>>(k->meq, k->mineq, k->rhs, ryc, ryd);
+  // A pending condensation is enqueued here (breakdowns surface at the next synchronous call, hb_lowrank_check). With the int8-slice
+  // kernel its row-maximum sweep over [J; S; Y] also produces tdot = [J; S; Y] (DhInv .* rx), and steps 1-2 collapse to
+  //   J (H+Dx)^{-1} rx = tdot_J - Z [sigma*tdot_S; tdot_Y],   Z = U V^{-1}  (U = [sigma J DhInv S^T, J DhInv Y^T], kept from the condensation)
+  // which is the same product with the low-rank correction applied on the m side: J is not read a second time.
+  bool fused = false;
+  if(!k->cond_valid) {
+    HB_CHECK(do_condense_async(k, rx));
+    fused = k->tdot_valid;
+    k->tdot_valid = false; // tied to this rx
+  }
+  if(fused) {
+    hb_phase_mark(c, HB_PH_HSOLVE1);
+    k_fused_rhs<<<(m + 127) / 128, 128, 0, c->stream>>>(m, k->meq, k->l, k->sigma, k->tdot, k->Z, ryc, ryd, k->rhs);
     HB_LAUNCHED();
+    hb_phase_mark(c, HB_PH_JX);
+  } else {
+    // 1. dx_tmp = (H+Dx)^{-1} rx                                  hiopKKTLinSys.cpp:1146
+    HB_CHECK(hess_solve(k, rx, dx));
+    hb_phase_mark(c, HB_PH_HSOLVE1);
+    if(m > 0) {
+      // 2. rhs = J*dx_tmp - [ryc; ryd]                              :1154-1157
+      HB_CHECK(gemv_rows(k, k->J, m, 0.0, k->rhs, 1.0, dx));
+      hb_phase_mark(c, HB_PH_JX);
+      k_sub_stacked<<<(m + 127) / 128, 128, 0, c->stream>>>(k->meq, k->mineq, k->rhs, ryc, ryd);
+      HB_LAUNCHED();
+    }
+  }
+  if(m > 0) {
     // 3. N dy = rhs with residual-driven refinement               :1169, 1192-1350
     HB_CHECK(hb_dense_spd_solve_refine2(c, m, k->F, m, k->have_finv ? k->Finv : nullptr, k->svec, k->Nmat, m, k->rhs, k->dy, k->work, 1e-8, 3,
                                         k->stats));

@@ -32,6 +32,8 @@ struct hb_lowrank
   bool check_pending = false; // an asynchronous condensation left its info words unchecked
   int fallbacks = 0;          // times the FP64 kernel had to redo an int8-slice condensation whose Cholesky broke down
   double* tri = nullptr;      // packed upper triangle of C_aug for the all-reduce
+  double* tdot = nullptr;     // [J; S; Y] (DhInv .* rx) from the fused row-maximum sweep of an int8-slice condensation (m + 2 lmax)
+  bool tdot_valid = false;
   // host staging (hb_lowrank_kkt_system_host)
   double* hbuf[16] = {nullptr};
   double* hJ = nullptr;

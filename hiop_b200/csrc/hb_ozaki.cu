@@ -112,6 +112,91 @@ k_oz_rowmax(const double* const* __restrict__ rowptr, int M, long long K, const 
   m = hb_warp_max(m);
   if((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(&mx[row], (unsigned long long)__double_as_longlong(m));
 }
+// Row maxima AND the row dot products with t = d .* x in the same pass over the rows (a5/a13: J (H+Dx)^-1-weighted rhs, step 2 of
+// solveCompressed, costs no second sweep over J when the condensation is pending anyway). A CTA owns RD_COLS columns: each lane keeps
+// the sqrt(d) and d.*x values of its columns in registers and the 16 warps stream the rows past them, RD_ROWS rows in flight per warp.
+// partial[chunk][row] is combined in a fixed order by k_oz_dot_final; the maxima go through the same order-independent atomicMax.
+constexpr int RD_THREADS = 512, RD_COLS = 256, RD_ROWS = 4;
+template <bool VEC>
+__global__ void __launch_bounds__(RD_THREADS)
+k_oz_rowmax_dot(const double* const* __restrict__ rowptr, int M, long long K, const double* __restrict__ d, const double* __restrict__ x,
+                unsigned long long* __restrict__ mx, double* __restrict__ partial)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long k0 = (long long)blockIdx.x * RD_COLS;
+  const int len = (int)min((long long)RD_COLS, K - k0);
+  double sd[8], w[8];
+  // slot p of a lane: VEC -> the pair of columns 2*(lane + 32*(p/2)) + (p&1); scalar -> column lane + 32*p (relative to k0)
+#define RD_OFF(p) (VEC ? 2 * (lane + 32 * ((p) >> 1)) + ((p) & 1) : lane + 32 * (p))
+#pragma unroll
+  for(int p = 0; p < 8; p++) {
+    const int off = RD_OFF(p);
+    if(off < len) {
+      const double dv = d ? d[k0 + off] : 1.0;
+      sd[p] = d ? sqrt(dv) : 1.0;
+      w[p] = dv * x[k0 + off];
+    } else {
+      sd[p] = 0.0;
+      w[p] = 0.0;
+    }
+  }
+  const int wstride = (RD_THREADS / 32) * gridDim.y;
+  for(int i0 = warp + (RD_THREADS / 32) * blockIdx.y; i0 < M; i0 += wstride * RD_ROWS) {
+    double v[RD_ROWS][8];
+#pragma unroll
+    for(int r = 0; r < RD_ROWS; r++) {
+      const int i = i0 + r * wstride;
+      const double* row = i < M ? rowptr[i] + k0 : nullptr;
+#pragma unroll
+      for(int p = 0; p < (VEC ? 4 : 8); p++) {
+        if(VEC) {
+          double2 t = make_double2(0.0, 0.0);
+          if(row && RD_OFF(2 * p) < len) t = *reinterpret_cast<const double2*>(row + RD_OFF(2 * p));
+          v[r][2 * p] = t.x;
+          v[r][2 * p + 1] = t.y;
+        } else {
+          v[r][p] = (row && RD_OFF(p) < len) ? row[RD_OFF(p)] : 0.0;
+        }
+      }
+    }
+#pragma unroll
+    for(int r = 0; r < RD_ROWS; r++) {
+      const int i = i0 + r * wstride;
+      double mm = 0.0, acc = 0.0;
+#pragma unroll
+      for(int p = 0; p < 8; p++) {
+        mm = fmax(mm, fabs(v[r][p]) * sd[p]);
+        acc += v[r][p] * w[p];
+      }
+      mm = hb_warp_max(mm);
+      acc = hb_warp_sum(acc);
+      if(lane == 0 && i < M) {
+        if(mm > 0.0) atomicMax(&mx[i], (unsigned long long)__double_as_longlong(mm));
+        partial[(size_t)blockIdx.x * M + i] = acc;
+      }
+    }
+  }
+#undef RD_OFF
+}
+// out[i] = sum_chunks partial[c][i]: 32 rows x 8 chunk classes per CTA, fixed-order combine
+__global__ void __launch_bounds__(256)
+k_oz_dot_final(int M, int nchunks, const double* __restrict__ partial, double* __restrict__ out)
+{
+  __shared__ double sm[8][33];
+  const int ri = threadIdx.x & 31, part = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ri;
+  double s = 0.0;
+  if(i < M)
+    for(int c = part; c < nchunks; c += 8) s += partial[(size_t)c * M + i];
+  sm[part][ri] = s;
+  __syncthreads();
+  if(part == 0 && i < M) {
+    double t = 0.0;
+#pragma unroll
+    for(int p = 0; p < 8; p++) t += sm[p][ri];
+    out[i] = t;
+  }
+}
 __global__ void k_oz_exponents(int M, const unsigned long long* __restrict__ mx, int* __restrict__ e)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -414,6 +499,8 @@ struct OzState
   unsigned long long* mx = nullptr;
   int* e = nullptr;
   int mcap = 0;
+  double* dot_partial = nullptr; // [chunks][M] partial row dots of the fused row-maximum pass
+  size_t dot_cap = 0;
   OzItem* d_items = nullptr;
   int2* d_tiles = nullptr;
   CUtensorMap mapA, mapB;
@@ -423,7 +510,7 @@ void oz_state_free(void* p)
 {
   OzState* st = static_cast<OzState*>(p);
   if(!st) return;
-  cudaFree(st->Q); cudaFree(st->sd); cudaFree(st->mx); cudaFree(st->e); cudaFree(st->d_items); cudaFree(st->d_tiles);
+  cudaFree(st->Q); cudaFree(st->sd); cudaFree(st->mx); cudaFree(st->e); cudaFree(st->d_items); cudaFree(st->d_tiles); cudaFree(st->dot_partial);
   delete st;
 }
 OzState& oz_state(hb_ctx* c)
@@ -453,7 +540,9 @@ int launch_gemm(hb_ctx* c, OzState& st, int chunk_blocks, double* partial)
 } // namespace
 
 // Same contract as hb_syrk_rows (C = A diag(d) A^T, both triangles), computed with S int8 slices on tcgen05.
-int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool rows_aligned16, const double* d, double* C, int ldc, int S)
+// dot_x/dot_out (optional, device): dot_out[i] = sum_k row_i[k] d[k] dot_x[k] over the local columns, produced by the row-maximum pass
+int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowptr_dev, bool rows_aligned16, const double* d, double* C, int ldc, int S,
+                       const double* dot_x, double* dot_out)
 {
   HB_REQUIRE(c && M >= 0 && K >= 0 && ldc >= M && (S == 6 || S == 7 || S == 8), "hb_syrk_rows_ozaki: bad arguments");
   if(M == 0) return HB_OK;
@@ -539,11 +628,31 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
   }
   HB_CUDA(cudaMemsetAsync(st.mx, 0, sizeof(unsigned long long) * Mpad, c->stream));
   {
-    long long gx = (K + 256 * 64 - 1) / (256 * 64);
-    if(gx < 1) gx = 1;
-    if(gx > 64) gx = 64;
-    k_oz_rowmax<<<dim3((unsigned)gx, M), 256, 0, c->stream>>>(rowptr_dev, M, K, sd, st.mx);
-    HB_LAUNCHED();
+    if(dot_x && dot_out && K > 0) {
+      const int nchunks = (int)((K + RD_COLS - 1) / RD_COLS);
+      if(st.dot_cap < (size_t)nchunks * M) {
+        HB_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(st.dot_partial);
+        HB_CUDA(cudaMalloc(&st.dot_partial, sizeof(double) * (size_t)nchunks * M));
+        st.dot_cap = (size_t)nchunks * M;
+      }
+      int rsplit = (2 * c->num_sms + nchunks - 1) / nchunks; // short shards: split the rows of a chunk over several CTAs
+      rsplit = rsplit < 1 ? 1 : (rsplit > 8 ? 8 : rsplit);
+      // pairs of columns need 16-byte aligned rows AND an even first column per lane (RD_COLS is even)
+      if(rows_aligned16 && (K & 1) == 0)
+        k_oz_rowmax_dot<true><<<dim3(nchunks, rsplit), RD_THREADS, 0, c->stream>>>(rowptr_dev, M, K, d, dot_x, st.mx, st.dot_partial);
+      else
+        k_oz_rowmax_dot<false><<<dim3(nchunks, rsplit), RD_THREADS, 0, c->stream>>>(rowptr_dev, M, K, d, dot_x, st.mx, st.dot_partial);
+      HB_LAUNCHED();
+      k_oz_dot_final<<<(M + 31) / 32, 256, 0, c->stream>>>(M, nchunks, st.dot_partial, dot_out);
+      HB_LAUNCHED();
+    } else {
+      long long gx = (K + 256 * 64 - 1) / (256 * 64);
+      if(gx < 1) gx = 1;
+      if(gx > 64) gx = 64;
+      k_oz_rowmax<<<dim3((unsigned)gx, M), 256, 0, c->stream>>>(rowptr_dev, M, K, sd, st.mx);
+      HB_LAUNCHED();
+    }
     k_oz_exponents<<<(Mpad + 127) / 128, 128, 0, c->stream>>>(M, st.mx, st.e);
     HB_LAUNCHED();
     const unsigned sx = (unsigned)((Kpad / 8 + 255) / 256);

@@ -151,9 +151,44 @@ def test_auto_mode_uses_global_n_and_falls_back_to_fp64(ctx):
     dx, dyc, dyd = [ctx.zeros(s) for s in (P2.n, P2.m_eq, P2.m_ineq)]
     assert k.solveCompressed(ctx.to_device(P2.rx), T["ryc"], T["ryd"], dx, dyc, dyd)
     k.check()
+    ctx.sync()
     Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P2.zl, P2.sxl, P2.zu, P2.sxu, P2.ixl, P2.ixu, P2.vl, P2.sdl, P2.vu, P2.sdu, P2.idl, P2.idu, P2.sigma)
     st = ko.QnState(P2.Jc, P2.Jd, DhInv, Dd_inv, P2.St, P2.Yt, P2.L, P2.D, P2.sigma)
     dxo, dyco, dydo, _ = ko.solve_compressed(st, P2.rx, P2.ryc, P2.ryd)
     assert np.abs(dx.cpu().numpy() - dxo).max() <= 1e-8 * np.abs(dxo).max()
     assert np.abs(dyd.cpu().numpy() - dydo).max() <= 1e-8 * max(1.0, np.abs(dydo).max())
     k.close()
+
+
+@pytest.mark.parametrize("n,m,l", [(40000, 90, 4), (33001, 70, 3), (40960, 64, 0), (300, 66, 2)])
+def test_fused_rowmax_sweep_delivers_the_same_direction(ctx, n, m, l):
+    """solveCompressed with a PENDING int8-slice condensation takes J (H+Dx)^-1 rx from the row-maximum sweep (tdot - Z p) instead of a
+    second pass over J; with the condensation already done it takes the two-pass route (hiopKKTLinSys.cpp:1146-1157). Same direction,
+    and both agree with the oracle's solveCompressed."""
+    P = synth.make_qn_problem(n, m, l, seed=n % 97)
+    res = {}
+    for fused in (True, False):
+        k, T = _setup(ctx, P, 8)
+        if not fused:
+            k.condense()                              # condensation no longer pending -> unfused steps 1-2
+        dx, dyc, dyd = [ctx.zeros(s) for s in (P.n, P.m_eq, P.m_ineq)]
+        assert k.solveCompressed(ctx.to_device(P.rx), T["ryc"], T["ryd"], dx, dyc, dyd)
+        k.check()
+        ctx.sync()                                    # check() only waits when a condensation was still unchecked
+        assert k.condense_mode_used() == 8
+        res[fused] = [v.cpu().numpy().copy() for v in (dx, dyc, dyd)]
+        # a second solve with another rhs on the same (valid) condensation must not reuse the dots of the first
+        rx2 = ctx.to_device(P.rx[::-1].copy())
+        dx2, dyc2, dyd2 = [ctx.zeros(s) for s in (P.n, P.m_eq, P.m_ineq)]
+        assert k.solveCompressed(rx2, T["ryc"], T["ryd"], dx2, dyc2, dyd2)
+        ctx.sync()
+        res[(fused, 2)] = dx2.cpu().numpy().copy()
+        k.close()
+    for a, b in zip(res[True], res[False]):
+        assert np.abs(a - b).max() <= 1e-10 * max(1.0, np.abs(b).max())
+    assert np.abs(res[(True, 2)] - res[(False, 2)]).max() <= 1e-10 * max(1.0, np.abs(res[(False, 2)]).max())
+    Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P.zl, P.sxl, P.zu, P.sxu, P.ixl, P.ixu, P.vl, P.sdl, P.vu, P.sdu, P.idl, P.idu, P.sigma)
+    st = ko.QnState(P.Jc, P.Jd, DhInv, Dd_inv, P.St, P.Yt, P.L, P.D, P.sigma)
+    dxo, dyco, dydo, _ = ko.solve_compressed(st, P.rx, P.ryc, P.ryd)
+    assert np.abs(res[True][0] - dxo).max() <= 1e-9 * max(1.0, np.abs(dxo).max())
+    assert np.abs(res[True][2] - dydo).max() <= 1e-9 * max(1.0, np.abs(dydo).max())
