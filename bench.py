@@ -632,6 +632,9 @@ def run_engine(args):
                        "timeline_ms_per_rank": [{q: round(v, 4) for q, v in t.items()} for t in timeline],
                        "kkt_residual_note": "max-norm residual of the compressed 3-block KKT system over max-norm rhs, evaluated with torch FP64 matmuls and a "
                                             "compact-BFGS operator assembled in bench.py (no hiop_b200 kernel, not the condensed matrix); gate 1e-8"},
+            "condensed_factor": {"kernel": "equilibrated Cholesky of the m x m condensed matrix N (replicated on every rank)", "N": m,
+                                 "ms": max(t["Cholesky"] for t in timeline),
+                                 "tflops": (m ** 3 / 3.0) / (max(t["Cholesky"] for t in timeline) * 1e-3) / 1e12 if m else 0.0},
             "clocks": main["clocks"], "gpu_launches": main["launches"], "roofline": roofline,
             "other_mode": {"condense_mode": "fp64_dmma" if other["mode"] == 0 else f"int8_slices_{other['mode']}", "value": 1e3 / other["ms_step"],
                            "ms_per_step": other["ms_step"], "kkt_residual_rel_independent_operators": kkt_resid_other, "roofline": kernel_roofline(other)},
