@@ -32,12 +32,7 @@ extern "C" int hb_ctx_create(int device, hb_ctx** out)
   hb_ctx* c = new hb_ctx;
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
-  {
-    // middle of the priority range: the dense factorizations put their panel chain above it, the int8-slice condensation its slicing below
-    int least = 0, greatest = 0;
-    HB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-    HB_CUDA(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, (least + greatest) / 2));
-  }
+  HB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   HB_CUDA(cudaMalloc(&c->red_dev, sizeof(double) * HB_RED_SLOTS));
   HB_CUDA(cudaMallocHost(&c->red_host, sizeof(double) * 64));
   *out = c;
@@ -75,7 +70,6 @@ extern "C" int hb_ctx_last_syrk_ms(hb_ctx* c, float* ms)
 {
   HB_REQUIRE(c && ms, "hb_ctx_last_syrk_ms: null argument");
   if(!c->timing || !c->syrk_timed) return hb_fail(HB_ERR_STATE, "hb_ctx_last_syrk_ms: no timed SYRK launch recorded%s", "");
-  if(c->syrk_ms_fn) return c->syrk_ms_fn(c, ms);
   HB_CUDA(cudaEventSynchronize(c->ev_syrk1));
   HB_CUDA(cudaEventElapsedTime(ms, c->ev_syrk0, c->ev_syrk1));
   return HB_OK;

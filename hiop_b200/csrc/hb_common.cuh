@@ -69,7 +69,6 @@ struct hb_ctx
   bool timing = false;
   cudaEvent_t ev_syrk0 = nullptr, ev_syrk1 = nullptr;
   bool syrk_timed = false;
-  int (*syrk_ms_fn)(hb_ctx*, float*) = nullptr; // set when the last timed condensation was a sequence of launches (int8-slice chunks)
   // phase timeline (hb_ctx_phase_timeline): events recorded at fixed points of one update + condense + solve when enabled
   bool phases = false;
   cudaEvent_t ev_phase[16] = {nullptr};

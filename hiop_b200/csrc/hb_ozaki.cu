@@ -87,12 +87,14 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_c, uint64_t da, uint64_t d
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0), "r"(0), "r"(0), "r"(0)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16])
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
-                 "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr));
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]),
+        "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+        "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -232,14 +234,13 @@ __device__ __forceinline__ void oz_digits(int v, int (&d)[ND])
 template <int S>
 __global__ void __launch_bounds__(256)
 k_oz_slice(const double* const* __restrict__ rowptr, int M, int Mpad, long long K, long long Kpad, const double* __restrict__ sd,
-           const int* __restrict__ e, int8_t* __restrict__ Q, int vec_ok, long long col0, long long col1)
+           const int* __restrict__ e, int8_t* __restrict__ Q, int vec_ok)
 {
   static_assert(S >= 5 && S <= 8, "slices");
   constexpr int NLO = S - 4;
   const int row = blockIdx.y;
-  // columns [col0, col1) of the padded range (col0 a multiple of 2048: one CTA = 2048 columns of one row)
-  const long long k0 = col0 + ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
-  if(k0 >= col1) return;
+  const long long k0 = ((long long)blockIdx.x * 256 + threadIdx.x) * 8;
+  if(k0 >= Kpad) return;
   double x[8];
 #pragma unroll
   for(int j = 0; j < 8; j++) x[j] = 0.0;
@@ -311,7 +312,7 @@ struct OzCfg
 // Per K block the B operand (S slices x 64 rows, 8S KB) is double-buffered and stays resident while the S A tiles (16 KB
 // each) stream through a ring; slice p is multiplied against the stacked slices 0..S-1-p of B (N up to 256 per MMA).
 template <int S>
-__global__ void __launch_bounds__(OZ_THREADS, 2) // 2: caps the kernel at 128 registers (shared memory still admits one CTA per SM)
+__global__ void __launch_bounds__(OZ_THREADS, 1)
 k_oz_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const OzItem* __restrict__ items, int n_items,
           int chunk_blocks, double* __restrict__ partial)
 {
@@ -425,38 +426,34 @@ k_oz_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
         mbar_wait_sleep(accfull, accphase);
         accphase ^= 1;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        // four quarters of 16 columns: 16 FP64 accumulators + 16 loaded words live at a time (the kernel stays at <= 128 registers per
-        // thread without spills, which leaves room on the SM for the slicing CTAs of the next column chunk, see hb_syrk_rows_ozaki)
-#pragma unroll 1
-        for(int c0 = 0; c0 < TN; c0 += 16) {
-          double acc[16];
+        double acc[TN];
 #pragma unroll
-          for(int j = 0; j < 16; j++) acc[j] = 0.0;
+        for(int j = 0; j < TN; j++) acc[j] = 0.0;
 #pragma unroll
-          for(int t = S - 1; t >= 0; t--) { // smallest weights first
-            const double wt = ldexp(1.0, -(12 + 7 * t));
-            uint32_t v[16];
-            tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(t * TN + c0), v);
+        for(int t = S - 1; t >= 0; t--) { // smallest weights first
+          const double wt = ldexp(1.0, -(12 + 7 * t));
+#pragma unroll
+          for(int c0 = 0; c0 < TN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(t * TN + c0), v);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-            for(int j = 0; j < 16; j++) acc[j] += (double)(int)v[j] * wt;
+            for(int j = 0; j < 32; j++) acc[c0 + j] += (double)(int)v[j] * wt;
           }
-          if(c0 + 16 >= TN) { // the accumulators are free again once the last quarter has been read
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            __syncwarp();
-            if(lane == 0) mbar_arrive(accempty);
-          }
-          if(c == 0) {
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+        __syncwarp();
+        if(lane == 0) mbar_arrive(accempty);
+        if(c == 0) {
 #pragma unroll
-            for(int j = 0; j < 16; j += 2) *reinterpret_cast<double2*>(slot + c0 + j) = make_double2(acc[j], acc[j + 1]);
-          } else {
+          for(int j = 0; j < TN; j += 2) *reinterpret_cast<double2*>(slot + j) = make_double2(acc[j], acc[j + 1]);
+        } else {
 #pragma unroll
-            for(int j = 0; j < 16; j += 2) {
-              double2 o = *reinterpret_cast<double2*>(slot + c0 + j);
-              o.x += acc[j];
-              o.y += acc[j + 1];
-              *reinterpret_cast<double2*>(slot + c0 + j) = o;
-            }
+          for(int j = 0; j < TN; j += 2) {
+            double2 o = *reinterpret_cast<double2*>(slot + j);
+            o.x += acc[j];
+            o.y += acc[j + 1];
+            *reinterpret_cast<double2*>(slot + j) = o;
           }
         }
       }
@@ -469,7 +466,7 @@ k_oz_gemm(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUte
 
 // C(i,j) = 2^{e_i+e_j} * sum over splits of the partial tiles; upper part computed, mirrored.
 __global__ void __launch_bounds__(256)
-k_oz_fixup(int M, int n_tiles, const int2* __restrict__ tile_ij, int splits, int nch, const double* __restrict__ partial, const int* __restrict__ e,
+k_oz_fixup(int M, int n_tiles, const int2* __restrict__ tile_ij, int splits, const double* __restrict__ partial, const int* __restrict__ e,
            double* __restrict__ C, int ldc)
 {
   const int t = blockIdx.x;
@@ -479,8 +476,7 @@ k_oz_fixup(int M, int n_tiles, const int2* __restrict__ tile_ij, int splits, int
     const int gi = ij.x * TM + r, gj = ij.y * TN + c;
     if(gi >= M || gj >= M || gj < gi) continue;
     double v = 0.0;
-    for(int ch = 0; ch < nch; ch++) // column chunks in order, then the K splits of a chunk: fixed order
-      for(int s = 0; s < splits; s++) v += partial[((size_t)((ch * n_tiles + t) * splits + s)) * (TM * TN) + el];
+    for(int s = 0; s < splits; s++) v += partial[((size_t)(t * splits + s)) * (TM * TN) + el];
     v = ldexp(v, e[gi] + e[gj]);
     C[(size_t)gi * ldc + gj] = v;
     C[(size_t)gj * ldc + gi] = v;
@@ -491,7 +487,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 PFN_encodeTiled g_encode = nullptr;
 
-constexpr int OZ_MAX_CH = 8;
 struct OzState
 {
   int M = -1, S = 0, splits = 0, n_tiles = 0, n_items = 0;
@@ -509,12 +504,6 @@ struct OzState
   OzItem* d_items = nullptr;
   int2* d_tiles = nullptr;
   CUtensorMap mapA, mapB;
-  // column-chunk pipeline: the slices of chunk c+1 are cut (low-priority side stream) while the tensor cores work on chunk c
-  int nch = 1;
-  long long chunk_col[OZ_MAX_CH + 1] = {0}; // chunk boundaries in columns (multiples of 2048)
-  cudaStream_t slice_stream = nullptr;
-  cudaEvent_t ev_ready = nullptr, ev_slice[OZ_MAX_CH] = {nullptr};
-  cudaEvent_t ev_g0[OZ_MAX_CH] = {nullptr}, ev_g1[OZ_MAX_CH] = {nullptr}; // timing of the GEMM launches (hb_ctx_enable_timing)
 };
 // one state per CONTEXT (it used to be per device: two contexts on one GPU would have shared the slice buffer across their streams)
 void oz_state_free(void* p)
@@ -522,13 +511,6 @@ void oz_state_free(void* p)
   OzState* st = static_cast<OzState*>(p);
   if(!st) return;
   cudaFree(st->Q); cudaFree(st->sd); cudaFree(st->mx); cudaFree(st->e); cudaFree(st->d_items); cudaFree(st->d_tiles); cudaFree(st->dot_partial);
-  if(st->slice_stream) cudaStreamDestroy(st->slice_stream);
-  if(st->ev_ready) cudaEventDestroy(st->ev_ready);
-  for(int q = 0; q < OZ_MAX_CH; q++) {
-    if(st->ev_slice[q]) cudaEventDestroy(st->ev_slice[q]);
-    if(st->ev_g0[q]) cudaEventDestroy(st->ev_g0[q]);
-    if(st->ev_g1[q]) cudaEventDestroy(st->ev_g1[q]);
-  }
   delete st;
 }
 OzState& oz_state(hb_ctx* c)
@@ -540,23 +522,8 @@ OzState& oz_state(hb_ctx* c)
   return *static_cast<OzState*>(c->oz_state);
 }
 
-// sum of the GEMM launch durations of the last condensation (events recorded around every chunk launch)
-int oz_gemm_ms(hb_ctx* c, float* ms)
-{
-  OzState& st = oz_state(c);
-  float tot = 0.f;
-  for(int q = 0; q < st.nch; q++) {
-    float t = 0.f;
-    HB_CUDA(cudaEventSynchronize(st.ev_g1[q]));
-    HB_CUDA(cudaEventElapsedTime(&t, st.ev_g0[q], st.ev_g1[q]));
-    tot += t;
-  }
-  *ms = tot;
-  return HB_OK;
-}
-
 template <int S>
-int launch_gemm(hb_ctx* c, OzState& st, int chunk_blocks, double* partial, int ch)
+int launch_gemm(hb_ctx* c, OzState& st, int chunk_blocks, double* partial)
 {
   const size_t smem = OzCfg<S>::SMEM;
   static bool attr[16] = {false}; // function attributes are per device
@@ -565,8 +532,7 @@ int launch_gemm(hb_ctx* c, OzState& st, int chunk_blocks, double* partial, int c
     if(c->device < 16) attr[c->device] = true;
   }
   const int G = st.n_items < c->num_sms ? st.n_items : c->num_sms;
-  k_oz_gemm<S><<<G, OZ_THREADS, smem, c->stream>>>(st.mapA, st.mapB, st.d_items + (size_t)ch * st.n_items, st.n_items, chunk_blocks,
-                                                   partial + (size_t)ch * st.n_items * (TM * TN));
+  k_oz_gemm<S><<<G, OZ_THREADS, smem, c->stream>>>(st.mapA, st.mapB, st.d_items, st.n_items, chunk_blocks, partial);
   HB_LAUNCHED();
   return HB_OK;
 }
@@ -624,42 +590,20 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
         if(bj * TN < M) tiles.push_back(make_int2(bi, bj));
     const int nt = (int)tiles.size();
     const long long kstages = Kpad / KS;
-    // column chunks: >= 192 K stages (24576 columns) each, at most OZ_MAX_CH, boundaries on multiples of 16 stages (2048 columns = one
-    // slicing CTA), partial-tile workspace bounded to 1 GB
-    static const int max_ch = getenv("HB_OZ_CHUNKS") ? atoi(getenv("HB_OZ_CHUNKS")) : OZ_MAX_CH;
-    int nch = (int)(kstages / 192);
-    if(nch > max_ch) nch = max_ch;
-    if(nch > OZ_MAX_CH) nch = OZ_MAX_CH;
-    if(nch < 1) nch = 1;
     int splits = c->num_sms / (nt > 0 ? nt : 1);
     if(splits < 1) splits = 1;
-    while(nch > 1 && (size_t)nch * nt * splits * TM * TN * sizeof(double) > ((size_t)1 << 30)) nch--;
-    long long cb[OZ_MAX_CH + 1];
-    for(int q = 0; q <= nch; q++) cb[q] = q == nch ? kstages : (hb_part_begin(kstages, nch, q) / 16) * 16;
-    if(splits > cb[1] - cb[0]) splits = (int)(cb[1] - cb[0]);
-    if(splits < 1) splits = 1;
+    if(splits > kstages) splits = (int)kstages;
     std::vector<OzItem> items;
-    // per chunk, split-major order: the CTAs of one split sweep the same K range concurrently (operand reuse in L2)
-    for(int q = 0; q < nch; q++)
-      for(int s = 0; s < splits; s++)
-        for(int t = 0; t < nt; t++) {
-          OzItem it;
-          it.bi = tiles[t].x; it.bj = tiles[t].y;
-          const long long len = cb[q + 1] - cb[q];
-          const long long b = cb[q] + hb_part_begin(len, splits, s), e2 = cb[q] + hb_part_begin(len, splits, s + 1);
-          it.k_begin = (int)b; it.k_count = (int)(e2 - b);
-          it.slot = t * splits + s; // within the chunk's block of partial tiles
-          items.push_back(it);
-        }
-    st.nch = nch;
-    for(int q = 0; q <= nch; q++) st.chunk_col[q] = cb[q] * KS;
-    if(nch > 1 && !st.slice_stream) {
-      int least = 0, greatest = 0;
-      HB_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-      HB_CUDA(cudaStreamCreateWithPriority(&st.slice_stream, cudaStreamNonBlocking, least));
-      HB_CUDA(cudaEventCreateWithFlags(&st.ev_ready, cudaEventDisableTiming));
-      for(int q = 0; q < OZ_MAX_CH; q++) HB_CUDA(cudaEventCreateWithFlags(&st.ev_slice[q], cudaEventDisableTiming));
-    }
+    // split-major order: the CTAs of one split sweep the same K range concurrently (operand reuse in L2)
+    for(int s = 0; s < splits; s++)
+      for(int t = 0; t < nt; t++) {
+        OzItem it;
+        it.bi = tiles[t].x; it.bj = tiles[t].y;
+        const long long b = hb_part_begin(kstages, splits, s), e2 = hb_part_begin(kstages, splits, s + 1);
+        it.k_begin = (int)b; it.k_count = (int)(e2 - b);
+        it.slot = t * splits + s;
+        items.push_back(it);
+      }
     cudaFree(st.d_items); cudaFree(st.d_tiles);
     HB_CUDA(cudaMalloc(&st.d_items, sizeof(OzItem) * items.size()));
     HB_CUDA(cudaMalloc(&st.d_tiles, sizeof(int2) * nt));
@@ -673,7 +617,7 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
     CUresult r2 = g_encode(&st.mapB, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, st.Q, dims, strides, boxB, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if(r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) return hb_fail(HB_ERR_CUDA, "cuTensorMapEncodeTiled failed%s", "");
-    st.M = M; st.K = K; st.S = S; st.Mpad = Mpad; st.Kpad = Kpad; st.splits = splits; st.n_tiles = nt; st.n_items = (int)items.size() / nch;
+    st.M = M; st.K = K; st.S = S; st.Mpad = Mpad; st.Kpad = Kpad; st.splits = splits; st.n_tiles = nt; st.n_items = (int)items.size();
   }
   // 1. sqrt(d), row maxima, exponents, slices
   const double* sd = nullptr;
@@ -711,50 +655,30 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
     }
     k_oz_exponents<<<(Mpad + 127) / 128, 128, 0, c->stream>>>(M, st.mx, st.e);
     HB_LAUNCHED();
+    const unsigned sx = (unsigned)((Kpad / 8 + 255) / 256);
+    const int vec_ok = rows_aligned16 ? 1 : 0;
+    if(S == 6) k_oz_slice<6><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
+    else if(S == 7) k_oz_slice<7><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
+    else k_oz_slice<8><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
+    HB_LAUNCHED();
   }
-  // 2. slices + tcgen05 GEMM into FP64 partial tiles, pipelined over column chunks: chunk q+1 is sliced on the side stream (HBM-bound,
-  //    40 registers, no shared memory: its CTAs fit beside the resident GEMM CTA of every SM) while chunk q is multiplied (tensor-bound,
-  //    ~10 % of the HBM bandwidth). Only the first chunk's slicing is exposed.
-  HB_CHECK(hb_ws_reserve(c, sizeof(double) * (size_t)st.nch * st.n_items * TM * TN));
+  // 2. tcgen05 GEMM into FP64 partial tiles
+  HB_CHECK(hb_ws_reserve(c, sizeof(double) * (size_t)st.n_items * TM * TN));
   // (t+1) * Kc * 2^12 < 2^31 with t+1 <= S  ->  Kc <= 2^19 / S columns
   int chunk_stages = (int)((524288 / S) / KS);
   // strict: S products of |q q'| <= 2^12 per column must stay BELOW 2^31 (S = 8 gives exactly 2^31 with 512 stages of 128 columns when
   // every digit is -64, see tests/test_cpu_oz_model.py)
   while((long long)S * chunk_stages * KS * 4096 >= (1LL << 31)) chunk_stages--;
-  const int vec_ok = rows_aligned16 ? 1 : 0;
-  cudaStream_t ss = st.nch > 1 ? st.slice_stream : c->stream;
-  if(st.nch > 1) {
-    HB_CUDA(cudaEventRecord(st.ev_ready, c->stream)); // exponents and sqrt(d) are ready; every earlier reader of Q has been enqueued before
-    HB_CUDA(cudaStreamWaitEvent(ss, st.ev_ready, 0));
-  }
-  for(int q = 0; q < st.nch; q++) {
-    const long long col0 = st.chunk_col[q], col1 = st.chunk_col[q + 1];
-    const unsigned sx = (unsigned)((col1 - col0 + 2047) / 2048);
-    if(S == 6) k_oz_slice<6><<<dim3(sx, Mpad), 256, 0, ss>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok, col0, col1);
-    else if(S == 7) k_oz_slice<7><<<dim3(sx, Mpad), 256, 0, ss>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok, col0, col1);
-    else k_oz_slice<8><<<dim3(sx, Mpad), 256, 0, ss>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok, col0, col1);
-    HB_LAUNCHED();
-    if(st.nch > 1) HB_CUDA(cudaEventRecord(st.ev_slice[q], ss));
-  }
-  if(c->timing && !st.ev_g0[0])
-    for(int q = 0; q < OZ_MAX_CH; q++) {
-      HB_CUDA(cudaEventCreate(&st.ev_g0[q]));
-      HB_CUDA(cudaEventCreate(&st.ev_g1[q]));
-    }
-  for(int q = 0; q < st.nch; q++) {
-    if(st.nch > 1) HB_CUDA(cudaStreamWaitEvent(c->stream, st.ev_slice[q], 0));
-    if(c->timing) HB_CUDA(cudaEventRecord(st.ev_g0[q], c->stream));
-    if(S == 6) HB_CHECK(launch_gemm<6>(c, st, chunk_stages, (double*)c->ws, q));
-    else if(S == 7) HB_CHECK(launch_gemm<7>(c, st, chunk_stages, (double*)c->ws, q));
-    else HB_CHECK(launch_gemm<8>(c, st, chunk_stages, (double*)c->ws, q));
-    if(c->timing) HB_CUDA(cudaEventRecord(st.ev_g1[q], c->stream));
-  }
+  if(c->timing) HB_CUDA(cudaEventRecord(c->ev_syrk0, c->stream));
+  if(S == 6) HB_CHECK(launch_gemm<6>(c, st, chunk_stages, (double*)c->ws));
+  else if(S == 7) HB_CHECK(launch_gemm<7>(c, st, chunk_stages, (double*)c->ws));
+  else HB_CHECK(launch_gemm<8>(c, st, chunk_stages, (double*)c->ws));
   if(c->timing) {
+    HB_CUDA(cudaEventRecord(c->ev_syrk1, c->stream));
     c->syrk_timed = true;
-    c->syrk_ms_fn = oz_gemm_ms; // the GEMM time is the sum over the chunk launches
   }
   // 3. split-K reduction, row scales, symmetrisation
-  k_oz_fixup<<<st.n_tiles, 256, 0, c->stream>>>(M, st.n_tiles, st.d_tiles, st.splits, st.nch, (const double*)c->ws, st.e, C, ldc);
+  k_oz_fixup<<<st.n_tiles, 256, 0, c->stream>>>(M, st.n_tiles, st.d_tiles, st.splits, (const double*)c->ws, st.e, C, ldc);
   HB_LAUNCHED();
   return HB_OK;
 }

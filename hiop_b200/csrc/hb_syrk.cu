@@ -520,7 +520,6 @@ int hb_syrk_rows(hb_ctx* c, int M, long long K, const double* const* rowptr_dev,
   if(c->timing) {
     HB_CUDA(cudaEventRecord(c->ev_syrk1, c->stream));
     c->syrk_timed = true;
-    c->syrk_ms_fn = nullptr;
   }
   k_syrk_fixup<<<dim3(S.ntiles, BM / 16), 256, 0, c->stream>>>(M, S.d_tile_ij, S.d_tile_slot_begin, S.d_tile_slots, (const double*)c->ws, C, ldc);
   HB_LAUNCHED();

@@ -22,7 +22,11 @@ def ctx():
 
 
 def _p(t):
-    return ctypes.c_void_p(t.data_ptr())
+    # the pointer object keeps its tensor alive: `_p(ctx.to_device(a))` as a call argument would otherwise free the block before the
+    # next argument is built, and torch's caching allocator may hand the same bytes out again
+    q = ctypes.c_void_p(t.data_ptr())
+    q._keep = t
+    return q
 
 
 def test_matrixTimesMatTrans(ctx):
@@ -148,8 +152,9 @@ def test_lowrank_test_direction(ctx):
     dWd = Bdx @ dx + ((Dx + dwx) * dx) @ dx + ((Dd + dwd) * dd) @ dd
     xs = dx @ dx + dd @ dd
     out = (ctypes.c_double * 2)()
+    dx_d, dd_d, dwx_d, dwd_d = D(dx), D(dd), D(dwx), D(dwd)   # kept alive: a pointer into a freed torch block may be handed out again
     for fact, deltas in ((1e-11, True), (1e30, True), (1e-11, False)):
-        rc = ctx.L.hb_lowrank_test_direction(k.h, _p(D(dx)), _p(D(dd)), _p(D(dwx)) if deltas else None, _p(D(dwd)) if deltas else None, fact, out)
+        rc = ctx.L.hb_lowrank_test_direction(k.h, _p(dx_d), _p(dd_d), _p(dwx_d) if deltas else None, _p(dwd_d) if deltas else None, fact, out)
         want = dWd if deltas else dWd - (dwx * dx) @ dx - (dwd * dd) @ dd
         assert rc == (0 if want < xs * fact else 1)
         # the compact form of B against the recursive one: 1e-10 (tests/test_gpu_parity.py), relative to the size of the three terms
