@@ -519,6 +519,25 @@ def run_engine(args):
             timeline = [None] * world
             dist.all_gather_object(timeline, tl)
 
+        # ---- phase split: the solve alone on the cached factor (second right-hand side of the same KKT matrix) ----
+        def solve_only():
+            rx_work.copy_(T["rx"])
+            assert k.solveCompressed(rx_work, T["ryc"], T["ryd"], dx, dyc, dyd)
+        for _ in range(3):
+            solve_only()
+        barrier()
+        es0, es1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        es0.record()
+        for _ in range(10):
+            solve_only()
+        es1.record()
+        barrier()
+        solve_only_ms = es0.elapsed_time(es1) / 10
+        if world > 1:
+            t = torch.tensor([solve_only_ms], dtype=torch.float64, device=ctx.device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            solve_only_ms = float(t.item())
+
         # ---- end to end through the host-buffer entry point (public API a HiOp adapter calls when mem_space is host) ----
         e2e = None
         # N>1: every rank uploads its own column shard from pinned host memory (bounded to 4 GB of pinned J per rank)
@@ -632,6 +651,9 @@ def run_engine(args):
                        "timeline_ms_per_rank": [{q: round(v, 4) for q, v in t.items()} for t in timeline],
                        "kkt_residual_note": "max-norm residual of the compressed 3-block KKT system over max-norm rhs, evaluated with torch FP64 matmuls and a "
                                             "compact-BFGS operator assembled in bench.py (no hiop_b200 kernel, not the condensed matrix); gate 1e-8"},
+            "phase_split": {"assemble+factor_ms": main["ms_step"] - solve_only_ms, "solve_on_cached_factor_ms": solve_only_ms,
+                            "note": "solve_on_cached_factor = solveCompressed with a valid condensation (two sweeps over J, SPD solve, two (H+Dx)^-1 "
+                                    "applications), timed separately over 10 calls; assemble+factor = step - that"},
             "condensed_factor": {"kernel": "equilibrated Cholesky of the m x m condensed matrix N (replicated on every rank)", "N": m,
                                  "ms": max(t["Cholesky"] for t in timeline),
                                  "tflops": (m ** 3 / 3.0) / (max(t["Cholesky"] for t in timeline) * 1e-3) / 1e12 if m else 0.0},
