@@ -35,6 +35,9 @@ private:
   int meq_, mineq_, lmax_;
   // device mirrors
   double *dJ_, *dSt_, *dYt_;
+  double* dsec_[4] = {nullptr, nullptr, nullptr, nullptr}; // x, grad_f, yc, yd of the iterate handed to the device-side secant update
+  bool secant_ready_ = false;
+  int n_secant_dev_ = 0;
   double *dpat_[4], *dit_[8], *drhs_[3], *dsol_[3];
   double *dres_[12], *ddir_[12]; // allocated on the first device-side refinement
   bool ir_on_device_;

@@ -2,10 +2,12 @@
 #include "hiopb200_hooks.hpp"
 #include "hiopLinSolverSymDenseB200.hpp"
 #include "hiopKKTLinSysLowRankB200.hpp"
+#include "hiopHessianLowRankB200.hpp"
 #include "hiopLinSolverSymDenseLapack.hpp"
 #include "hiopNlpFormulation.hpp"
 #include "hiopIterate.hpp"
 #include "hiopResidual.hpp"
+#include "LinAlgFactory.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -68,6 +70,51 @@ hiopLinSolverSymDense* hiop_b200_new_symdense_solver(int n, hiopNlpFormulation* 
 {
   if(hiop_b200_enabled()) return new hiopLinSolverSymDenseB200(n, nlp, safe_mode);
   return new hiopLinSolverSymDenseLapack(n, nlp);
+}
+
+hiopMatrix* hiop_b200_new_hessian_lowrank(hiopNlpDenseConstraints* nlp, int max_memory_length)
+{
+  if(hiop_b200_enabled()) return new hiopHessianLowRankB200(nlp, max_memory_length);
+  return new hiopHessianLowRank(nlp, max_memory_length);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+hiopHessianLowRankB200::hiopHessianLowRankB200(hiopNlpDenseConstraints* nlp, int max_memory_length)
+  : hiopHessianLowRank(nlp, max_memory_length), device_mode_(false), pending_(0)
+{
+  const char* e = getenv("HIOP_B200_SECANT");
+  const char* ir = getenv("HIOP_B200_IR");
+  // the host-side BiCGStab of HIOP_B200_IR=host applies this object's timesVec, which needs S_t / Y_t on the host
+  device_mode_ = e && !strcmp(e, "device") && !(ir && !strcmp(ir, "host")) && max_memory_length <= 64;
+}
+
+bool hiopHessianLowRankB200::update(const hiopIterate& x_curr, const hiopVector& grad_f_curr, const hiopMatrix& Jac_c_curr,
+                                    const hiopMatrix& Jac_d_curr)
+{
+  if(!device_mode_) return hiopHessianLowRank::update(x_curr, grad_f_curr, Jac_c_curr, Jac_d_curr);
+  pending_++; // carried out by hiopKKTLinSysLowRankB200::update, which receives the same arguments next (hiopAlgFilterIPM.cpp:1215-1216)
+  return true;
+}
+
+double hiopHessianLowRankB200::sigma0_value() const { return sigma0; }
+int hiopHessianLowRankB200::sigma_strategy_value() const { return sigma_update_strategy; }
+
+void hiopHessianLowRankB200::mirror(int l, double sigma_new, const double* L_host, const double* D_host)
+{
+  sigma = sigma_new;
+  l_curr = l;
+  // L_ (l x l) and D_ (l) are resized by the base class as the memory grows (growL / growD, hiopHessianLowRank.cpp:779-823); here they
+  // are re-created at the mirrored size
+  if(L_->m() != l) {
+    delete L_;
+    delete D_;
+    L_ = LinearAlgebraFactory::create_matrix_dense("DEFAULT", l, l);
+    D_ = LinearAlgebraFactory::create_vector("DEFAULT", l);
+  }
+  if(l > 0) {
+    memcpy(L_->local_data(), L_host, sizeof(double) * (size_t)l * l);
+    memcpy(D_->local_data(), D_host, sizeof(double) * (size_t)l);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -166,12 +213,13 @@ hiopKKTLinSysLowRankB200::~hiopKKTLinSysLowRankB200()
   if(getenv("HIOP_B200_STATS") && n_updates_ > 0) {
     // per-iteration KKT time of the engine path, next to the reference's own tmSolverInternal / time_kkt output
     fprintf(stderr, "hiop-b200 stats: updates %d, Jacobian uploads %d (first %.0f bytes, after the first %.0f bytes), KKT update+condense %.3f ms/it, "
-            "directions %.3f ms/call (%d calls)\n", n_updates_, n_jac_uploads_, jac_bytes_first_, jac_bytes_later_, 1e3 * t_update_ / n_updates_,
-            n_dirs_ ? 1e3 * t_dirs_ / n_dirs_ : 0.0, n_dirs_);
+            "directions %.3f ms/call (%d calls), secant updates on the device %d\n", n_updates_, n_jac_uploads_, jac_bytes_first_, jac_bytes_later_,
+            1e3 * t_update_ / n_updates_, n_dirs_ ? 1e3 * t_dirs_ / n_dirs_ : 0.0, n_dirs_, n_secant_dev_);
   }
   if(h_) hb_lowrank_destroy(h_);
   if(!ctx_) return;
   hb_free(ctx_, dJ_); hb_free(ctx_, dSt_); hb_free(ctx_, dYt_);
+  for(auto* p : dsec_) if(p) hb_free(ctx_, p);
   for(auto* p : dpat_) hb_free(ctx_, p);
   for(auto* p : dit_) hb_free(ctx_, p);
   for(auto* p : drhs_) hb_free(ctx_, p);
@@ -219,15 +267,41 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
     jac_hash_ = hash;
     if(!ok(hb_lowrank_set_jacobian(h_, dJ_, dJ_ + (size_t)meq_ * n_), "hb_lowrank_set_jacobian", &healthy_)) return false;
   }
-  // secant memory as hiopHessianLowRank::update left it (hiopHessianLowRank.cpp:262-388)
-  const int l = Hess->St_->m();
-  if(l > 0) {
-    upload(dSt_, Hess->St_->local_data_const(), (size_t)l * n_);
-    upload(dYt_, Hess->Yt_->local_data_const(), (size_t)l * n_);
+  hiopHessianLowRankB200* hdev = dynamic_cast<hiopHessianLowRankB200*>(Hess);
+  if(hdev && hdev->device_mode()) {
+    // a11 on the device: the iterate(s) hiopHessianLowRankB200::update noted are applied here, with the Jacobian registered just above
+    if(!secant_ready_) {
+      if(!ok(hb_lowrank_secant_reset(h_, hdev->sigma0_value(), hdev->sigma_strategy_value()), "hb_lowrank_secant_reset", &healthy_)) return false;
+      for(int i = 0; i < 2; i++)
+        if(!ok(hb_malloc(ctx_, sizeof(double) * (size_t)(n_ > 0 ? n_ : 1), (void**)&dsec_[i]), "hb_malloc(secant)", &healthy_)) return false;
+      if(!ok(hb_malloc(ctx_, sizeof(double) * (size_t)(meq_ > 0 ? meq_ : 1), (void**)&dsec_[2]), "hb_malloc(secant)", &healthy_)) return false;
+      if(!ok(hb_malloc(ctx_, sizeof(double) * (size_t)(mineq_ > 0 ? mineq_ : 1), (void**)&dsec_[3]), "hb_malloc(secant)", &healthy_)) return false;
+      secant_ready_ = true;
+    }
+    if(hdev->take_pending() > 0) {
+      upload(dsec_[0], iter->x->local_data_const(), n_);
+      upload(dsec_[1], grad_f->local_data_const(), n_);
+      upload(dsec_[2], iter->yc->local_data_const(), meq_);
+      upload(dsec_[3], iter->yd->local_data_const(), mineq_);
+      int status = 0;
+      if(!ok(hb_lowrank_secant_update(h_, dsec_[0], dsec_[1], dsec_[2], dsec_[3], 0, &status), "hb_lowrank_secant_update", &healthy_)) return false;
+      int l = 0;
+      double sg = 0.0, Lh[64 * 64], Dh[64];
+      if(!ok(hb_lowrank_secant_state(h_, &l, &sg, nullptr, nullptr, Lh, Dh), "hb_lowrank_secant_state", &healthy_)) return false;
+      hdev->mirror(l, sg, Lh, Dh);
+      n_secant_dev_++;
+    }
+  } else {
+    // secant memory as hiopHessianLowRank::update left it on the host (hiopHessianLowRank.cpp:262-388)
+    const int l = Hess->St_->m();
+    if(l > 0) {
+      upload(dSt_, Hess->St_->local_data_const(), (size_t)l * n_);
+      upload(dYt_, Hess->Yt_->local_data_const(), (size_t)l * n_);
+    }
+    if(!ok(hb_lowrank_set_secant(h_, l, Hess->sigma, dSt_, dYt_, l ? Hess->L_->local_data_const() : nullptr, l ? Hess->D_->local_data_const() : nullptr),
+           "hb_lowrank_set_secant", &healthy_))
+      return false;
   }
-  if(!ok(hb_lowrank_set_secant(h_, l, Hess->sigma, dSt_, dYt_, l ? Hess->L_->local_data_const() : nullptr, l ? Hess->D_->local_data_const() : nullptr),
-         "hb_lowrank_set_secant", &healthy_))
-    return false;
   const hiopVector* blocks[8] = {iter->zl, iter->sxl, iter->zu, iter->sxu, iter->vl, iter->sdl, iter->vu, iter->sdu};
   for(int i = 0; i < 8; i++) upload(dit_[i], blocks[i]->local_data_const(), blocks[i]->get_size());
   if(!healthy_) return false;

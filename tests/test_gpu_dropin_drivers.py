@@ -118,7 +118,7 @@ def _run_env(exe, args, env_extra, cwd=None):
     if not os.path.exists(path):
         pytest.skip(f"{exe} not built (oracle/_ref travels from the build container)")
     env = dict(os.environ)
-    for k in ("HIOP_B200", "HB_CONDENSE", "HIOP_B200_STATS"):
+    for k in ("HIOP_B200", "HB_CONDENSE", "HIOP_B200_STATS", "HIOP_B200_SECANT"):
         env.pop(k, None)
     env.update(env_extra)
     p = subprocess.run([path] + args, capture_output=True, text=True, env=env, timeout=900, cwd=cwd)
@@ -178,6 +178,29 @@ def test_exM_iterate_sequence_both_condensation_kernels(n, m):
         worst, rows = _tables_agree(tabs[mode], tabs["dmma"], until_linesearch_differs=True)
         assert worst <= 1e-5, (mode, worst)
         assert rows >= min(25, len(tabs["dmma"])), (mode, rows)
+
+
+@pytest.mark.parametrize("exe,args", [("exM_b200.exe", ["33000", "64"]), ("exM_b200.exe", ["1000", "50"]), ("ex2_b200.exe", ["5000", "-unconstrained", "-selfcheck"]),
+                                      ("ex1_b200.exe", ["50000", "1.0", "-selfcheck"])])
+def test_secant_memory_on_the_device(exe, args):
+    """a11 inside the drop-in (HIOP_B200_SECANT=device): hiopHessianLowRankB200::update only notes the iterate, the KKT adapter hands it to
+    hb_lowrank_secant_update, S_t / Y_t / x_prev / grad_prev / J_prev never leave HBM. Same iterate table as the reference (1e-5 rule up to
+    the first flipped line-search decision), same optimum, and every accepted iterate went through the device-side update."""
+    rc_r, out_r, _, tab_r = _run_env(exe, args, {})
+    assert rc_r == 0, out_r[-1500:]
+    rc_b, out_b, err_b, tab_b = _run_env(exe, args, {"HIOP_B200": "1", "HIOP_B200_SECANT": "device", "HIOP_B200_STATS": "1"})
+    assert rc_b == 0, (out_b[-1500:], err_b[-800:])
+    m = re.search(r"updates (\d+), .*secant updates on the device (\d+)", err_b)
+    assert m and int(m.group(2)) == int(m.group(1)) > 3, err_b[-800:]
+    worst, rows = _tables_agree(tab_b, tab_r, until_linesearch_differs=True)
+    assert worst <= 1e-5, worst
+    assert rows >= min(25, len(tab_r)), (rows, len(tab_r))
+    assert abs(len(tab_b) - len(tab_r)) <= 2, (len(tab_b), len(tab_r))
+    if "-selfcheck" in args:                      # the drivers return non-zero when their selfcheck fails (rc checked above)
+        assert "selfcheck" in out_b
+    else:
+        obj = [float(re.search(r"objective=([-+0-9.e]+)", o).group(1)) for o in (out_b, out_r)]
+        assert abs(obj[0] - obj[1]) <= 1e-8 * abs(obj[1]), obj
 
 
 def test_exM_jacobian_is_uploaded_once():
