@@ -77,7 +77,9 @@ extern "C" int hb_ctx_last_syrk_ms(hb_ctx* c, float* ms)
 
 // Timeline of one quasi-Newton step: with on != 0 the engine records an event after each phase of hb_lowrank_update / condense /
 // solve_compressed; hb_ctx_phase_timeline(ctx, 0, ms) waits for them and returns the phase durations (ms) in the order
-// update, C_aug (slicing + GEMM), all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce), SPD solve, J^T dy, H^-1 rx (second).
+// update, row maxima (+ fused row dots), slicing, GEMM + fix-up [= C_aug; the first two only with the int8-slice kernel, otherwise the whole
+// condensation is in the third], all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce), SPD solve, J^T dy, H^-1 rx (second).
+// A mark that was not passed contributes 0 and its time is counted in the next recorded phase.
 extern "C" int hb_ctx_phase_timeline(hb_ctx* c, int on, float* ms_host10)
 {
   HB_REQUIRE(c, "null ctx");
@@ -91,9 +93,12 @@ extern "C" int hb_ctx_phase_timeline(hb_ctx* c, int on, float* ms_host10)
   c->phases = false;
   if(ms_host10) {
     HB_CUDA(cudaStreamSynchronize(c->stream));
+    int prev = (c->phase_mask & 1u) ? 0 : -1;
     for(int i = 1; i < HB_PH_COUNT; i++) {
       ms_host10[i - 1] = 0.f;
-      if((c->phase_mask >> i & 1u) && (c->phase_mask >> (i - 1) & 1u)) HB_CUDA(cudaEventElapsedTime(&ms_host10[i - 1], c->ev_phase[i - 1], c->ev_phase[i]));
+      if(!(c->phase_mask >> i & 1u)) continue;
+      if(prev >= 0) HB_CUDA(cudaEventElapsedTime(&ms_host10[i - 1], c->ev_phase[prev], c->ev_phase[i]));
+      prev = i;
     }
   }
   return HB_OK;

@@ -86,7 +86,7 @@ static constexpr int HB_RED_SLOTS = 4096;
 int hb_ws_reserve(hb_ctx* ctx, size_t bytes);
 
 // phase marks of the quasi-Newton step (ids are the HB_PH_* below); a no-op unless hb_ctx_phase_timeline switched them on
-enum { HB_PH_START = 0, HB_PH_UPDATE, HB_PH_CAUG, HB_PH_ALLREDUCE, HB_PH_VN, HB_PH_CHOL, HB_PH_HSOLVE1, HB_PH_JX, HB_PH_SPDSOLVE, HB_PH_JTY, HB_PH_HSOLVE2, HB_PH_COUNT };
+enum { HB_PH_START = 0, HB_PH_UPDATE, HB_PH_OZ_ROWMAX, HB_PH_OZ_SLICE, HB_PH_CAUG, HB_PH_ALLREDUCE, HB_PH_VN, HB_PH_CHOL, HB_PH_HSOLVE1, HB_PH_JX, HB_PH_SPDSOLVE, HB_PH_JTY, HB_PH_HSOLVE2, HB_PH_COUNT };
 inline void hb_phase_mark(hb_ctx* c, int id)
 {
   if(c->phases && c->ev_phase[id]) {

@@ -655,12 +655,14 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
     }
     k_oz_exponents<<<(Mpad + 127) / 128, 128, 0, c->stream>>>(M, st.mx, st.e);
     HB_LAUNCHED();
+    hb_phase_mark(c, HB_PH_OZ_ROWMAX);
     const unsigned sx = (unsigned)((Kpad / 8 + 255) / 256);
     const int vec_ok = rows_aligned16 ? 1 : 0;
     if(S == 6) k_oz_slice<6><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
     else if(S == 7) k_oz_slice<7><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
     else k_oz_slice<8><<<dim3(sx, Mpad), 256, 0, c->stream>>>(rowptr_dev, M, Mpad, K, Kpad, sd, st.e, st.Q, vec_ok);
     HB_LAUNCHED();
+    hb_phase_mark(c, HB_PH_OZ_SLICE);
   }
   // 2. tcgen05 GEMM into FP64 partial tiles
   HB_CHECK(hb_ws_reserve(c, sizeof(double) * (size_t)st.n_items * TM * TN));

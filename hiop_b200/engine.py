@@ -62,15 +62,15 @@ class Context:
     def sync(self):
         check(self.L.hb_ctx_sync(self.h), "hb_ctx_sync")
 
-    PHASES = ("update", "C_aug (slicing+GEMM)", "all-reduce", "V/U/N assembly", "Cholesky", "H^-1 rx", "J dx (+all-reduce)", "SPD solve", "J^T dy",
-              "H^-1 rx (2nd)")
+    PHASES = ("update", "row maxima (+fused row dots)", "slicing", "GEMM+fix-up (C_aug)", "all-reduce", "V/U/N assembly", "Cholesky", "H^-1 rx",
+              "J dx (+all-reduce)", "SPD solve", "J^T dy", "H^-1 rx (2nd)")
 
     def phase_timeline(self, on: bool):
         """arm (on=True) / read (on=False -> dict phase -> ms) the per-phase event marks of one quasi-Newton step"""
         if on:
             check(self.L.hb_ctx_phase_timeline(self.h, 1, None), "hb_ctx_phase_timeline")
             return None
-        ms = (ctypes.c_float * 10)()
+        ms = (ctypes.c_float * len(self.PHASES))()
         check(self.L.hb_ctx_phase_timeline(self.h, 0, ms), "hb_ctx_phase_timeline")
         return {name: float(ms[i]) for i, name in enumerate(self.PHASES)}
 

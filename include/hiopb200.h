@@ -61,8 +61,8 @@ int hb_ctx_device(hb_ctx* ctx);
 int hb_ctx_enable_timing(hb_ctx* ctx, int on);
 /* Per-phase timeline of one quasi-Newton step (per-rank evidence for the multi-GPU runs): hb_ctx_phase_timeline(ctx, 1, NULL) arms the
  * marks, the next hb_lowrank_update + condense + solve_compressed records an event after each phase, hb_ctx_phase_timeline(ctx, 0, ms)
- * returns 10 durations in ms: update, C_aug (slicing + GEMM), all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce),
- * SPD solve, J^T dy, H^-1 rx (second). */
+ * returns 12 durations in ms: update, row maxima (+ fused row dots), slicing, GEMM + fix-up (the whole condensation with the FP64 kernel),
+ * all-reduce, V/U/N assembly, Cholesky, H^-1 rx, J dx (+ all-reduce), SPD solve, J^T dy, H^-1 rx (second). */
 int hb_ctx_phase_timeline(hb_ctx* ctx, int on, float* ms_host10);
 int hb_ctx_last_syrk_ms(hb_ctx* ctx, float* ms_host);
 
