@@ -175,17 +175,25 @@ k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, doub
     PROF(0);
     factor_diag(S, k0, info, b == 0, timing ? prof : nullptr);
     PROF(1);
-    if(b == 0) {
-      for(int e = tid; e < nb * nb; e += CT) {
-        const int j = e / nb, i = e % nb;
-        if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DS + i];
+    // CTA 0 stores the factored block -- but only after the next grid barrier: every CTA loaded the UNFACTORED block at the top of this
+    // iteration and nothing orders a slow CTA's load before an in-place store made right here (the factor stays in S.D until then)
+    auto store_diag = [&]() {
+      if(b == 0) {
+        for(int e = tid; e < nb * nb; e += CT) {
+          const int j = e / nb, i = e % nb;
+          if(i >= j) LC(A, lda, k0 + i, k0 + j) = S.D[j * DS + i];
+        }
+        if(invd)
+          for(int e = tid; e < 4 * 16 * 17; e += CT) invd[(size_t)(k0 / CB) * (4 * 16 * 17) + e] = S.Inv[e];
       }
-      if(invd)
-        for(int e = tid; e < 4 * 16 * 17; e += CT) invd[(size_t)(k0 / CB) * (4 * 16 * 17) + e] = S.Inv[e];
-    }
+    };
     const int r0 = k0 + nb;
     const int R = N - r0;
-    if(R <= 0) break;
+    if(R <= 0) {
+      grid.sync();
+      store_diag();
+      break;
+    }
     // ---- (2) my rows of L21 = A21 L11^-T ----
     {
       const int per = (R + G - 1) / G;
@@ -240,6 +248,7 @@ k_chol_coop(double* __restrict__ A, int lda, int N, int* __restrict__ info, doub
     }
     PROF(2);
     grid.sync();
+    store_diag();
     PROF(3);
     // ---- (3) trailing update: Lc(i,j) -= sum_p L21[i][p] L21[j][p] on the lower triangle, 64 x 64 tiles round-robin ----
     {
@@ -371,7 +380,8 @@ __device__ void block_solve(SolveSmem& S, bool trans)
   }
 }
 
-__device__ void load_block(SolveSmem& S, const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd, const double* __restrict__ v, int k0)
+// v is updated by other CTAs between the grid barriers of coop_potrs: no read-only promise on it, loads go to L2
+__device__ void load_block(SolveSmem& S, const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd, const double* v, int k0)
 {
   const int tid = threadIdx.x;
   const int nb = min(CB, N - k0);
@@ -380,13 +390,18 @@ __device__ void load_block(SolveSmem& S, const double* __restrict__ F, int ldf, 
     const int j = e / CB, i = e % CB;
     S.L[j * DS + i] = (i < nb && j < nb && i >= j) ? LC(F, ldf, k0 + i, k0 + j) : 0.0;
   }
-  if(tid < CB) S.z[tid] = tid < nb ? v[k0 + tid] : 0.0;
+  if(tid < CB) S.z[tid] = tid < nb ? __ldcg(v + k0 + tid) : 0.0;
   __syncthreads();
 }
 
-// v <- F^-T F^-1 v (v in global memory, length N)
+// v <- F^-T F^-1 v (v, w in global memory, length N; w is scratch).
+// Every CTA reads the current 64-entry block, solves it redundantly and updates its slice of the remaining entries; ONE CTA stores the
+// solved block. That store must not land where a slower CTA may still be reading the unsolved block of the same step (there is no grid
+// barrier between the read and the store): the forward sweep therefore reads v and stores its solved blocks into w, the backward sweep
+// reads w and stores into v. (The first version stored in place; a late CTA then occasionally loaded already-solved entries, the first
+// solve came out wrong and the refinement loop repaired it -- one extra correction and last-bit differences from run to run.)
 __device__ void coop_potrs(SolveSmem& S, cg::grid_group& grid, const double* __restrict__ F, int ldf, int N, const double* __restrict__ invd,
-                           double* __restrict__ v)
+                           double* v, double* w)
 {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, G = gridDim.x, b = blockIdx.x;
   const int nblk = (N + CB - 1) / CB;
@@ -402,24 +417,24 @@ __device__ void coop_potrs(SolveSmem& S, cg::grid_group& grid, const double* __r
         double acc = 0.0;
         for(int q = lane; q < nb; q += 32) acc += LC(F, ldf, r, k0 + q) * S.z[q];
         acc = hb_warp_sum(acc);
-        if(lane == 0) v[r] -= acc;
+        if(lane == 0) v[r] = __ldcg(v + r) - acc;
       }
     }
-    if(b == 0 && tid < nb) v[k0 + tid] = S.z[tid];
+    if(b == 0 && tid < nb) w[k0 + tid] = S.z[tid];
     grid.sync();
   }
-  for(int kb = nblk - 1; kb >= 0; kb--) { // backward: L^T x = z
+  for(int kb = nblk - 1; kb >= 0; kb--) { // backward: L^T x = z (z in w)
     const int k0 = kb * CB, nb = min(CB, N - k0);
-    load_block(S, F, ldf, N, invd, v, k0);
+    load_block(S, F, ldf, N, invd, w, k0);
     block_solve(S, true);
     if(k0 > 0) {
       const int per = (k0 + G - 1) / G;
       const int first = b * per, last = min(k0, first + per);
-      for(int cix = first + warp; cix < last; cix += CT / 32) { // one warp per column: v[c] -= L[k0:k0+nb, c] . x_k (contiguous)
+      for(int cix = first + warp; cix < last; cix += CT / 32) { // one warp per column: w[c] -= L[k0:k0+nb, c] . x_k (contiguous)
         double acc = 0.0;
         for(int q = lane; q < nb; q += 32) acc += LC(F, ldf, k0 + q, cix) * S.z[q];
         acc = hb_warp_sum(acc);
-        if(lane == 0) v[cix] -= acc;
+        if(lane == 0) w[cix] = __ldcg(w + cix) - acc;
       }
     }
     if(b == 0 && tid < nb) v[k0 + tid] = S.z[tid];
@@ -442,8 +457,8 @@ k_spd_solve_coop(const double* __restrict__ F, int ldf, int N, const double* __r
   for(int i = gtid; i < N; i += gthreads) v[i] = rhs[i] * s[i];
   if(gtid < 2) nrm_bits[gtid] = 0ull;
   grid.sync();
-  coop_potrs(S, grid, F, ldf, N, invd, v);
-  for(int i = gtid; i < N; i += gthreads) x[i] = v[i] * s[i];
+  coop_potrs(S, grid, F, ldf, N, invd, v, r); // r is free until the first residual
+  for(int i = gtid; i < N; i += gthreads) x[i] = __ldcg(v + i) * s[i];
   grid.sync();
   int nref = 0;
   double nrm = 0.0;
@@ -454,7 +469,7 @@ k_spd_solve_coop(const double* __restrict__ F, int ldf, int N, const double* __r
     for(int i = b * (CT / 32) + warp; i < N; i += G * (CT / 32)) {
       double acc = 0.0;
       const double* row = Nref + (size_t)i * ldn;
-      for(int j = lane; j < N; j += 32) acc += row[j] * x[j];
+      for(int j = lane; j < N; j += 32) acc += row[j] * __ldcg(x + j);
       acc = hb_warp_sum(acc);
       const double ri = rhs[i] - acc;
       if(lane == 0) r[i] = ri;
@@ -468,10 +483,10 @@ k_spd_solve_coop(const double* __restrict__ F, int ldf, int N, const double* __r
     nrm = __longlong_as_double((long long)*slot);
     if(!(nrm >= tol) || nrm > 1.7e308 || nref >= max_refine) break;
     if(gtid == 0) nrm_bits[(nref + 1) & 1] = 0ull; // the other slot is idle until the next round's barrier
-    for(int i = gtid; i < N; i += gthreads) v[i] = r[i] * s[i];
+    for(int i = gtid; i < N; i += gthreads) v[i] = __ldcg(r + i) * s[i];
     grid.sync();
-    coop_potrs(S, grid, F, ldf, N, invd, v);
-    for(int i = gtid; i < N; i += gthreads) x[i] += v[i] * s[i];
+    coop_potrs(S, grid, F, ldf, N, invd, v, r); // the residual has been consumed (v = r .* s above)
+    for(int i = gtid; i < N; i += gthreads) x[i] += __ldcg(v + i) * s[i];
     grid.sync();
     nref++;
   }
