@@ -25,6 +25,10 @@ public:
   bool device_mode() const { return device_mode_; }
   /// number of update() calls since the last take_pending(); the KKT adapter performs them on the device
   int take_pending() { const int p = pending_; pending_ = 0; return p; }
+  /// gradient of the objective handed to the last update(): the KKT update() cannot supply it -- the reference's non-virtual wrapper
+  /// forwards its own (never set) member instead of the argument (src/Optimization/hiopKKTLinSys.hpp:404)
+  const hiopVector* pending_grad_f() const { return pending_grad_f_; }
+  const hiopIterate* pending_iterate() const { return pending_it_; }
   /// B0 scaling and its update rule as read from the options by the base class (hiopHessianLowRank.cpp:118-136)
   double sigma0_value() const;
   int sigma_strategy_value() const;
@@ -34,5 +38,7 @@ public:
 private:
   bool device_mode_;
   int pending_;
+  const hiopVector* pending_grad_f_ = nullptr;
+  const hiopIterate* pending_it_ = nullptr;
 };
 } // namespace hiop

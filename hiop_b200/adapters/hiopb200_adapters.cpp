@@ -92,7 +92,9 @@ bool hiopHessianLowRankB200::update(const hiopIterate& x_curr, const hiopVector&
                                     const hiopMatrix& Jac_d_curr)
 {
   if(!device_mode_) return hiopHessianLowRank::update(x_curr, grad_f_curr, Jac_c_curr, Jac_d_curr);
-  pending_++; // carried out by hiopKKTLinSysLowRankB200::update, which receives the same arguments next (hiopAlgFilterIPM.cpp:1215-1216)
+  pending_++; // carried out by hiopKKTLinSysLowRankB200::update, which is called with the same iterate next (hiopAlgFilterIPM.cpp:1215-1216)
+  pending_grad_f_ = &grad_f_curr;
+  pending_it_ = &x_curr;
   return true;
 }
 
@@ -268,6 +270,9 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
     if(!ok(hb_lowrank_set_jacobian(h_, dJ_, dJ_ + (size_t)meq_ * n_), "hb_lowrank_set_jacobian", &healthy_)) return false;
   }
   hiopHessianLowRankB200* hdev = dynamic_cast<hiopHessianLowRankB200*>(Hess);
+  static const bool trace = getenv("HIOP_B200_TRACE") != nullptr;
+#define TR(msg) do { if(trace) { fprintf(stderr, "hiop-b200 trace: %s\n", msg); fflush(stderr); } } while(0)
+  TR("update: secant stage");
   if(hdev && hdev->device_mode()) {
     // a11 on the device: the iterate(s) hiopHessianLowRankB200::update noted are applied here, with the Jacobian registered just above
     if(!secant_ready_) {
@@ -277,18 +282,30 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
       if(!ok(hb_malloc(ctx_, sizeof(double) * (size_t)(meq_ > 0 ? meq_ : 1), (void**)&dsec_[2]), "hb_malloc(secant)", &healthy_)) return false;
       if(!ok(hb_malloc(ctx_, sizeof(double) * (size_t)(mineq_ > 0 ? mineq_ : 1), (void**)&dsec_[3]), "hb_malloc(secant)", &healthy_)) return false;
       secant_ready_ = true;
+      TR("secant reset done");
     }
-    if(hdev->take_pending() > 0) {
-      upload(dsec_[0], iter->x->local_data_const(), n_);
-      upload(dsec_[1], grad_f->local_data_const(), n_);
-      upload(dsec_[2], iter->yc->local_data_const(), meq_);
-      upload(dsec_[3], iter->yd->local_data_const(), mineq_);
+    const int pend = hdev->take_pending();
+    if(pend > 0) {
+      const hiopIterate* its = hdev->pending_iterate();
+      const hiopVector* gs = hdev->pending_grad_f();
+      if(!its || !gs) {
+        nlp_->log->printf(hovError, "hiopKKTLinSysLowRankB200::update: the quasi-Newton update did not leave its iterate / gradient\n");
+        return false;
+      }
+      upload(dsec_[0], its->x->local_data_const(), n_);
+      upload(dsec_[1], gs->local_data_const(), n_);
+      upload(dsec_[2], its->yc->local_data_const(), meq_);
+      upload(dsec_[3], its->yd->local_data_const(), mineq_);
       int status = 0;
+      TR("secant uploads done");
       if(!ok(hb_lowrank_secant_update(h_, dsec_[0], dsec_[1], dsec_[2], dsec_[3], 0, &status), "hb_lowrank_secant_update", &healthy_)) return false;
+      TR("secant update done");
       int l = 0;
       double sg = 0.0, Lh[64 * 64], Dh[64];
       if(!ok(hb_lowrank_secant_state(h_, &l, &sg, nullptr, nullptr, Lh, Dh), "hb_lowrank_secant_state", &healthy_)) return false;
+      TR("secant state read");
       hdev->mirror(l, sg, Lh, Dh);
+      TR("mirrored");
       n_secant_dev_++;
     }
   } else {
@@ -302,6 +319,7 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
            "hb_lowrank_set_secant", &healthy_))
       return false;
   }
+  TR("update: iterate upload");
   const hiopVector* blocks[8] = {iter->zl, iter->sxl, iter->zu, iter->sxu, iter->vl, iter->sdl, iter->vu, iter->sdu};
   for(int i = 0; i < 8; i++) upload(dit_[i], blocks[i]->local_data_const(), blocks[i]->get_size());
   if(!healthy_) return false;
@@ -310,7 +328,9 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
   // outer BiCGStab then reuses it (the reference rebuilds and refactorizes N on each solveCompressed call).
   // HB_ERR_NUMERIC (V singular / N not SPD, after the engine's own FP64 retry) is the reference's "update failed": return false and let
   // the driver escalate (hiopAlgFilterIPM.cpp:1216-1229); the adapter stays usable.
+  TR("update: condense");
   const int rc = hb_lowrank_condense(h_);
+  TR("update: condensed");
   t_update_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   n_updates_++;
   nlp_->runStats.tmSolverInternal.stop();
