@@ -341,6 +341,8 @@ bool hiopKKTLinSysLowRankB200::update(const hiopIterate* iter, const hiopVector*
   return true;
 }
 
+#undef TR
+
 bool hiopKKTLinSysLowRankB200::solveCompressed(hiopVector& rx, hiopVector& ryc, hiopVector& ryd, hiopVector& dx, hiopVector& dyc,
                                                hiopVector& dyd)
 {
