@@ -53,3 +53,26 @@ def test_truncated_product_error_against_fp64(S, tol):
     ref = B @ B.T
     assert np.abs(C - ref).max() <= tol * np.abs(ref).max()
     assert np.array_equal(C, C.T)                            # symmetric by construction (same integer products both ways)
+
+
+def test_fused_sweep_identity_for_step_2_of_solveCompressed():
+    """The identity behind k_oz_rowmax_dot: with t = [J; S; Y] (DhInv .* rx),
+    J (H+Dx)^-1 rx = t_J - Z [sigma t_S; t_Y],  Z = U V^-1,  U = [sigma J DhInv S^T, J DhInv Y^T]
+    -- checked against the oracle's own hess_solve + J product (hiopKKTLinSys.cpp:1146-1157, hiopHessianLowRank.cpp:495-540)."""
+    from hiop_b200 import synth
+    from oracle import kkt_oracle as ko
+    for n, m, l in ((3000, 25, 5), (1200, 40, 1), (900, 10, 0)):
+        P = synth.make_qn_problem(n, m, l, seed=3 + l)
+        Dx, DhInv, Dd, Dd_inv = ko.kkt_update(P.zl, P.sxl, P.zu, P.sxu, P.ixl, P.ixu, P.vl, P.sdl, P.vu, P.sdu, P.idl, P.idu, P.sigma)
+        st = ko.QnState(P.Jc, P.Jd, DhInv, Dd_inv, P.St, P.Yt, P.L, P.D, P.sigma)
+        want = st.J @ ko.hess_solve(st, P.rx)
+        w = DhInv * P.rx
+        t_J = st.J @ w
+        got = t_J
+        if l:
+            _, _, S1, Y1 = ko.condense(st)
+            U = np.hstack([S1, Y1])                              # S1 already carries sigma
+            Z = st.Vfac.solve(U.T.copy()).T                      # m x 2l
+            p = np.concatenate([P.sigma * (P.St @ w), P.Yt @ w])
+            got = t_J - Z @ p
+        assert np.abs(got - want).max() <= 1e-11 * max(1.0, np.abs(want).max())
