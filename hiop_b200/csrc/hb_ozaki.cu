@@ -590,19 +590,27 @@ int hb_syrk_rows_ozaki(hb_ctx* c, int M, long long K, const double* const* rowpt
         if(bj * TN < M) tiles.push_back(make_int2(bi, bj));
     const int nt = (int)tiles.size();
     const long long kstages = Kpad / KS;
-    // K splits: the persistent CTAs take the nt * splits items round-robin, so the makespan is ceil(nt * splits / SMs) / splits of one
-    // tile's full-K time. A single wave (splits = SMs / nt) is only one candidate: nt = 90 tiles (m = 1024) would keep 90 of 148 SMs
-    // busy; 8 splits give 720 items = 4.9 waves = 0.625 against the ideal 90/148 = 0.61. Bounds: >= 64 K stages per split, partial-tile
-    // workspace <= 1 GB, at most 16 splits; ties go to the smaller count.
-    int splits = 1;
+    // K splits. Default: one wave, splits = SMs / tiles (every CTA gets one item; 72 tiles x 2 splits = 144 of 148 SMs at m = 1000).
+    // Where that leaves the machine badly filled (81 tiles at m = 1024: one split, 81 of 148 SMs busy) several waves of the persistent
+    // CTAs are considered: the makespan is ceil(tiles * splits / SMs) / splits of one tile's full-K time, e.g. 9 splits = 729 items = 4.9
+    // waves -> 0.556 against the ideal 81/148 = 0.547. Bounds there: >= 64 K stages per split, partial-tile workspace <= 1 GB, <= 16
+    // splits; ties go to the smaller count.
+    int splits = c->num_sms / (nt > 0 ? nt : 1);
+    if(splits < 1) splits = 1;
+    if(splits > kstages) splits = (int)(kstages > 0 ? kstages : 1);
     {
-      double best = 1e30;
-      const int smax = getenv("HB_OZ_MAX_SPLITS") ? atoi(getenv("HB_OZ_MAX_SPLITS")) : 16;
-      for(int sp = 1; sp <= smax && nt > 0; sp++) {
-        if(sp > 1 && (kstages / sp < 64 || (size_t)nt * sp * TM * TN * sizeof(double) > ((size_t)1 << 30))) break;
-        const long long waves = ((long long)nt * sp + c->num_sms - 1) / c->num_sms;
-        const double cost = (double)waves / sp;
-        if(cost < best * (1.0 - 1e-3)) { best = cost; splits = sp; }
+      const long long items0 = (long long)nt * splits;
+      const long long waves0 = (items0 + c->num_sms - 1) / c->num_sms;
+      const double util0 = nt > 0 ? (double)items0 / (double)(waves0 * c->num_sms) : 1.0;
+      if(util0 < 0.7) {
+        double best = (double)waves0 / splits;
+        const int smax = getenv("HB_OZ_MAX_SPLITS") ? atoi(getenv("HB_OZ_MAX_SPLITS")) : 16;
+        for(int sp = 1; sp <= smax; sp++) {
+          if(sp > 1 && (kstages / sp < 64 || (size_t)nt * sp * TM * TN * sizeof(double) > ((size_t)1 << 30))) break;
+          const long long waves = ((long long)nt * sp + c->num_sms - 1) / c->num_sms;
+          const double cost = (double)waves / sp;
+          if(cost < best * (1.0 - 1e-3)) { best = cost; splits = sp; }
+        }
       }
     }
     if(splits > kstages) splits = (int)(kstages > 0 ? kstages : 1);
