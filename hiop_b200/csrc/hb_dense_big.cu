@@ -725,7 +725,9 @@ k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
       v[q] = (r < nrows && j < k0) ? LC(F, ldf, k0 + r, j) : 0.0;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if(tid < 64) S.xs[tid] = (jb + tid < k0) ? x[jb + tid] : 0.0;
+    // x is written by the tail CTA of EARLIER steps (other SMs, overlapping grids under programmatic dependent launch): read it from L2,
+    // never from a line this SM's L1 may still hold from before (a vector that is not 128-byte aligned lets a line straddle k0)
+    if(tid < 64) S.xs[tid] = (jb + tid < k0) ? __ldcg(x + jb + tid) : 0.0;
     __syncthreads();
     double acc = 0.0;
 #pragma unroll
@@ -752,7 +754,7 @@ k_solve_fwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
     inv[q] = cc <= r ? Inv[cc * BB + r] : 0.0;
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
+  const double xk = (tid < nrows) ? __ldcg(x + k0 + tid) : 0.0;
   wait_counter(counter, G);
   gather_partials(S, partial, G, nrows, xk);
   double acc = 0.0;
@@ -791,7 +793,7 @@ k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
       v[q] = (i < N && jl < nrows) ? LC(F, ldf, i, k0 + jl) : 0.0;
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    const double xi = i < N ? x[i] : 0.0;
+    const double xi = i < N ? __ldcg(x + i) : 0.0;
 #pragma unroll
     for(int q = 0; q < 8; q++) v[q] = hb_warp_sum(v[q] * xi);
     if(lane == 0) {
@@ -819,7 +821,7 @@ k_solve_bwd_step(const double* __restrict__ F, long long ldf, int N, int k0, con
       it[t * 4 + u] = rr >= cc ? Inv[cc * BB + rr] : 0.0;
     }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  const double xk = (tid < nrows) ? x[k0 + tid] : 0.0;
+  const double xk = (tid < nrows) ? __ldcg(x + k0 + tid) : 0.0;
   wait_counter(counter, G);
   gather_partials(S, partial, G, nrows, xk);
 #pragma unroll
